@@ -1,0 +1,15 @@
+// Error reporting for the C ABI (thread-local message buffer).
+#include "common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[512] = "";
+
+void apb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* apb_last_error(void) { return g_err; }
+extern "C" int apb_abi_version(void) { return 1; }

@@ -1,0 +1,210 @@
+// TokenLabelCrossEntropy: dense token-label CE + class-token CE, forward AND gradient in one pass.
+//
+// Replaces loss/cross_entropy.py:136-156 (+ SoftTargetCrossEntropy :30-36):
+//   L = (w_cls/B) sum_b CE(x_cls[b], t_cls[b]) + (w_dense/(B N)) sum_{b,n} CE(x_aux[b,n], target[b,:,2+n])
+//   CE(x,t) = -sum_c t_c log_softmax(x)_c ;  dL/dx = w * (softmax(x) * sum_c t_c - t)            
+//   t_cls[b] = lam * target[b,:,1] + (1-lam) * target[B-1-b,:,1]  when lam = 1 - box_area/N < 1   (:149-151)
+// The target is CLASS-major [B, C, 2+N] while the logits are token-major [B, N, C]; a CTA stages
+// TT tokens x C classes of both in shared memory (one HBM read of each), so the transpose happens
+// on chip and each logit / target element is read once and each gradient element written once.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TT = 16;        // tokens per CTA
+constexpr int TS = TT + 1;    // padded token stride of the staged target tile (bank-conflict free transposed reads)
+constexpr int NTHREADS = 256;
+
+struct TlceParams {
+  const void* x_cls;   // [B, C]
+  const void* x_aux;   // [B, N, C]
+  const float* target; // 3-D: [B, C, 2+N]   2-D: [B, C]
+  void* d_cls;
+  void* d_aux;
+  float* partial;      // [gridDim.x] per-CTA loss partials (already weighted)
+  int B, N, C;
+  long long t_sb, t_sc, t_ss;  // target strides (batch, class, slot); 2-D target: (C, 1, 0)
+  int slot_cls, slot_aux0;     // 3-D: 1, 2   2-D: 0, 0
+  float lam;                   // cls-target mix factor (>= 1 -> no mixing)
+  float w_cls, w_dense;        // already divided by B and B*N
+  int tiles_per_img;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS) tlce_kernel(TlceParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.C, N = p.N;
+  __shared__ float s_loss[NTHREADS / 32];
+  float my_loss = 0.f;
+  const int n_aux_ctas = p.B * p.tiles_per_img;
+
+  if ((int)blockIdx.x < n_aux_ctas) {
+    // ---------------- dense part: TT tokens of one image ----------------
+    const int b = blockIdx.x / p.tiles_per_img;
+    const int n0 = (blockIdx.x % p.tiles_per_img) * TT;
+    const int nt = min(TT, N - n0);
+    float* st = reinterpret_cast<float*>(smem_raw);                       // [C][TS]
+    T* sx = reinterpret_cast<T*>(smem_raw + (size_t)C * TS * sizeof(float));  // [TT][C]
+    const T* xg = reinterpret_cast<const T*>(p.x_aux) + ((size_t)b * N + n0) * C;
+    T* dg = reinterpret_cast<T*>(p.d_aux) + ((size_t)b * N + n0) * C;
+    // logits tile: nt*C contiguous elements
+    const size_t tot = (size_t)nt * C;
+    constexpr int VN = Vec16<T>::N;
+    if ((C % VN) == 0) {
+      for (size_t e = (size_t)tid * VN; e < tot; e += (size_t)NTHREADS * VN) {
+        Vec16<T> v;
+        v.load(xg + e);
+        v.store(sx + e);
+      }
+    } else {
+      for (size_t e = tid; e < tot; e += NTHREADS) sx[e] = xg[e];
+    }
+    // target tile: for each class, nt consecutive slots
+    const float* tg = p.target + (size_t)b * p.t_sb + (size_t)(p.slot_aux0 + n0) * p.t_ss;
+    for (int e = tid; e < C * TT; e += NTHREADS) {
+      const int c = e / TT, n = e % TT;
+      st[c * TS + n] = (n < nt) ? tg[(size_t)c * p.t_sc + (size_t)n * p.t_ss] : 0.f;
+    }
+    __syncthreads();
+    for (int n = warp; n < nt; n += NTHREADS / 32) {
+      const T* xr = sx + (size_t)n * C;
+      float m = -INFINITY;
+      for (int c = lane; c < C; c += 32) m = fmaxf(m, to_f(xr[c]));
+      m = warp_max(m);
+      float se = 0.f, sum_t = 0.f, sum_tx = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float x = to_f(xr[c]), t = st[c * TS + n];
+        se += expf(x - m);
+        sum_t += t;
+        sum_tx = fmaf(t, x, sum_tx);
+      }
+      se = warp_sum(se);
+      sum_t = warp_sum(sum_t);
+      sum_tx = warp_sum(sum_tx);
+      const float lse = m + logf(se);
+      if (lane == 0) my_loss += p.w_dense * (lse * sum_t - sum_tx);
+      T* dr = dg + (size_t)n * C;
+      for (int c = lane; c < C; c += 32) {
+        const float x = to_f(xr[c]), t = st[c * TS + n];
+        dr[c] = from_f<T>(p.w_dense * (expf(x - lse) * sum_t - t));
+      }
+    }
+  } else {
+    // ---------------- class-token part: one image per warp ----------------
+    const int b0 = ((int)blockIdx.x - n_aux_ctas) * (NTHREADS / 32);
+    const int b = b0 + warp;
+    if (b < p.B) {
+      const T* xr = reinterpret_cast<const T*>(p.x_cls) + (size_t)b * C;
+      T* dr = reinterpret_cast<T*>(p.d_cls) + (size_t)b * C;
+      const float* t0 = p.target + (size_t)b * p.t_sb + (size_t)p.slot_cls * p.t_ss;
+      const float* t1 = p.target + (size_t)(p.B - 1 - b) * p.t_sb + (size_t)p.slot_cls * p.t_ss;
+      const bool mix = p.lam < 1.f;
+      float m = -INFINITY;
+      for (int c = lane; c < C; c += 32) m = fmaxf(m, to_f(xr[c]));
+      m = warp_max(m);
+      float se = 0.f, sum_t = 0.f, sum_tx = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float x = to_f(xr[c]);
+        float t = t0[(size_t)c * p.t_sc];
+        if (mix) t = p.lam * t + (1.f - p.lam) * t1[(size_t)c * p.t_sc];
+        se += expf(x - m);
+        sum_t += t;
+        sum_tx = fmaf(t, x, sum_tx);
+      }
+      se = warp_sum(se);
+      sum_t = warp_sum(sum_t);
+      sum_tx = warp_sum(sum_tx);
+      const float lse = m + logf(se);
+      if (lane == 0) my_loss += p.w_cls * (lse * sum_t - sum_tx);
+      for (int c = lane; c < C; c += 32) {
+        const float x = to_f(xr[c]);
+        float t = t0[(size_t)c * p.t_sc];
+        if (mix) t = p.lam * t + (1.f - p.lam) * t1[(size_t)c * p.t_sc];
+        dr[c] = from_f<T>(p.w_cls * (expf(x - lse) * sum_t - t));
+      }
+    }
+  }
+  if (lane == 0) s_loss[warp] = my_loss;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < NTHREADS / 32; ++i) s += s_loss[i];
+    p.partial[blockIdx.x] = s;
+  }
+}
+
+// deterministic final reduction of the per-CTA partials (fixed tree order)
+__global__ void __launch_bounds__(256) tlce_reduce_kernel(const float* __restrict__ partial, int n, float* loss) {
+  __shared__ double s[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += (double)partial[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = (float)s[0];
+}
+
+template <typename T>
+__global__ void scale_by_scalar_kernel(const T* __restrict__ in, T* __restrict__ out, size_t n, const float* scalar) {
+  const float s = *scalar;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = from_f<T>(to_f(in[i]) * s);
+}
+
+}  // namespace
+
+// workspace: floats, at least apb_tlce_workspace_floats(B, N) entries.
+long long apb_tlce_workspace_floats(int B, int N) {
+  return (long long)B * ((N + TT - 1) / TT) + (B + NTHREADS / 32 - 1) / (NTHREADS / 32);
+}
+
+int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, int target_is_3d, int B, int N, int C,
+                     int box_area, float w_cls, float w_dense, float* loss, void* d_cls, void* d_aux, float* workspace,
+                     int dtype, apb_stream_t stream) {
+  cudaStream_t st = APB_STREAM(stream);
+  APB_CHECK_ARG(B > 0 && N > 0 && C > 0, APB_ERR_SHAPE, "tlce: bad shape B=%d N=%d C=%d", B, N, C);
+  APB_CHECK_ARG(dtype == APB_F32 || dtype == APB_BF16, APB_ERR_DTYPE, "tlce: dtype %d", dtype);
+  TlceParams p;
+  p.x_cls = x_cls; p.x_aux = x_aux; p.target = target; p.d_cls = d_cls; p.d_aux = d_aux; p.partial = workspace;
+  p.B = B; p.N = N; p.C = C;
+  if (target_is_3d) { p.t_sb = (long long)C * (2 + N); p.t_sc = 2 + N; p.t_ss = 1; p.slot_cls = 1; p.slot_aux0 = 2; }
+  else { p.t_sb = C; p.t_sc = 1; p.t_ss = 0; p.slot_cls = 0; p.slot_aux0 = 0; }
+  p.lam = 1.f - (float)((double)box_area / (double)N);
+  p.w_cls = w_cls / (float)B;
+  p.w_dense = w_dense / ((float)B * (float)N);
+  p.tiles_per_img = (N + TT - 1) / TT;
+  const int n_cls_ctas = (B + NTHREADS / 32 - 1) / (NTHREADS / 32);
+  const int grid = B * p.tiles_per_img + n_cls_ctas;
+  const size_t esz = dtype == APB_F32 ? 4 : 2;
+  const size_t smem = (size_t)C * TS * sizeof(float) + (size_t)TT * C * esz;
+  APB_CHECK_ARG(smem <= 227 * 1024, APB_ERR_UNSUPPORTED, "tlce: C=%d needs %zu B of shared memory (> 227 KB)", C, smem);
+  cudaError_t e;
+  if (dtype == APB_F32) {
+    e = cudaFuncSetAttribute(tlce_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { apb_set_error("tlce: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    tlce_kernel<float><<<grid, NTHREADS, smem, st>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(tlce_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { apb_set_error("tlce: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+    tlce_kernel<bf16><<<grid, NTHREADS, smem, st>>>(p);
+  }
+  APB_LAUNCH_CHECK("tlce_kernel");
+  tlce_reduce_kernel<<<1, 256, 0, st>>>(workspace, grid, loss);
+  APB_LAUNCH_CHECK("tlce_reduce");
+  return 0;
+}
+
+// out = in * (*scalar)  (backward of the fused loss: grads were produced for upstream gradient 1)
+int apb_scale_by_scalar(const void* in, void* out, long long n, const float* scalar, int dtype, apb_stream_t stream) {
+  cudaStream_t st = APB_STREAM(stream);
+  if (n <= 0) return 0;
+  const int grid = (int)((n + 1023) / 1024 > 148 * 8 ? 148 * 8 : (n + 1023) / 1024);
+  if (dtype == APB_F32) scale_by_scalar_kernel<float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, (size_t)n, scalar);
+  else scale_by_scalar_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)in, (bf16*)out, (size_t)n, scalar);
+  APB_LAUNCH_CHECK("scale_by_scalar");
+  return 0;
+}

@@ -1,0 +1,304 @@
+"""Thin tensor-level wrappers over the C ABI (no autograd here; see ops.py).
+
+Every function takes/returns contiguous CUDA tensors, allocates outputs with torch's caching allocator,
+launches on torch's current stream and raises `KernelError` on failure.  No CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import check, lib
+
+F32, BF16 = 0, 1
+_CODES = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def dt(t: torch.Tensor) -> int:
+    try:
+        return _CODES[t.dtype]
+    except KeyError:
+        raise TypeError(f'autoprog_b200 kernels support float32 / bfloat16 tensors, got {t.dtype}') from None
+
+
+def _p(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('autoprog_b200 kernels need CUDA tensors (there is no CPU fallback)')
+    if not t.is_contiguous():
+        raise RuntimeError(f'autoprog_b200 kernels need contiguous tensors, got strides {t.stride()} for shape {tuple(t.shape)}')
+    return t.data_ptr()
+
+
+def _st() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------ outlook attention core
+def outlook_fwd(v: torch.Tensor, logits: torch.Tensor, heads: int, scale: float, simt: bool = False) -> torch.Tensor:
+    B, H, W, Cc = v.shape
+    assert Cc == heads * 32, 'OutlookAttention kernels are built for head_dim 32'
+    assert logits.shape == (B, (H + 1) // 2, (W + 1) // 2, heads * 81) and logits.dtype == v.dtype
+    y = torch.empty_like(v)
+    fn = lib().apb_outlook_fwd_simt if simt else lib().apb_outlook_fwd
+    check(fn(_p(v), _p(logits), _p(y), B, H, W, heads, scale, dt(v), _st()), 'outlook_fwd')
+    return y
+
+
+def outlook_bwd(v, logits, dy, heads: int, scale: float, simt: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    B, H, W, _ = v.shape
+    dv = torch.empty_like(v)
+    dl = torch.empty_like(logits)
+    fn = lib().apb_outlook_bwd_simt if simt else lib().apb_outlook_bwd
+    check(fn(_p(v), _p(logits), _p(dy), _p(dv), _p(dl), B, H, W, heads, scale, dt(v), _st()), 'outlook_bwd')
+    return dv, dl
+
+
+# ------------------------------------------------------------------ token-label CE
+def tlce_fwd_bwd(x_cls, x_aux, target, box_area: int, w_cls: float, w_dense: float):
+    B, N, Cc = x_aux.shape
+    assert x_cls.shape == (B, Cc) and x_cls.dtype == x_aux.dtype
+    assert target.dtype == torch.float32
+    is3d = target.dim() == 3
+    assert tuple(target.shape) == ((B, Cc, 2 + N) if is3d else (B, Cc)), f'target shape {tuple(target.shape)}'
+    loss = torch.empty((), device=x_aux.device, dtype=torch.float32)
+    d_cls = torch.empty_like(x_cls)
+    d_aux = torch.empty_like(x_aux)
+    ws = torch.empty(int(lib().apb_tlce_workspace_floats(B, N)), device=x_aux.device, dtype=torch.float32)
+    check(lib().apb_tlce_fwd_bwd(_p(x_cls), _p(x_aux), _p(target), int(is3d), B, N, Cc, int(box_area), w_cls, w_dense,
+                                 _p(loss), _p(d_cls), _p(d_aux), _p(ws), dt(x_aux), _st()), 'tlce_fwd_bwd')
+    return loss, d_cls, d_aux
+
+
+def scale_by_scalar(x: torch.Tensor, scalar: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(x)
+    s = scalar.to(torch.float32).reshape(1).contiguous()
+    check(lib().apb_scale_by_scalar(_p(x), _p(out), x.numel(), _p(s), dt(x), _st()), 'scale_by_scalar')
+    return out
+
+
+# ------------------------------------------------------------------ layer norm (+ residual)
+def ln_fwd(x, gamma, beta, eps: float, out_dtype, r=None, rs=None, rows_per_sample: int = 1, want_sum: bool = False,
+           want_y: bool = True):
+    """xs = x + rs[b]*r ; y = LN(xs).  Returns (xs or None, y or None, mean, rstd)."""
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    xs = torch.empty_like(x) if (want_sum or r is not None) else None
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype) if want_y else None
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    if r is not None:
+        assert r.shape == x.shape and r.dtype == out_dtype
+    check(lib().apb_ln_fwd(_p(x), _p(r), _p(rs), rows_per_sample, _p(gamma), _p(beta), _p(xs), _p(y), _p(mean), _p(rstd),
+                           rows, Cc, eps, dt(x), _CODES[out_dtype], _st()), 'ln_fwd')
+    return xs, y, mean, rstd
+
+
+def ln_bwd(dy, xs, mean, rstd, gamma, dres=None, want_dr: bool = False, rs=None, rows_per_sample: int = 1):
+    """Returns (dxs, dr, dgamma, dbeta); dxs = dres + LN'(dy) (stream dtype of xs); dr = rs[b]*dxs in dy's dtype."""
+    Cc = xs.shape[-1]
+    rows = xs.numel() // Cc
+    dxs = torch.empty_like(xs)
+    dg = torch.empty(Cc, device=xs.device, dtype=torch.float32)
+    db = torch.empty(Cc, device=xs.device, dtype=torch.float32)
+    ws = torch.empty(int(lib().apb_ln_bwd_workspace_floats(Cc)), device=xs.device, dtype=torch.float32)
+    if dres is not None:
+        assert dres.dtype == xs.dtype and dres.shape == xs.shape
+    dr = torch.empty(xs.shape, device=xs.device, dtype=dy.dtype) if want_dr else None
+    check(lib().apb_ln_bwd(_p(dy), _p(xs), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dxs), _p(dr), _p(rs), rows_per_sample,
+                           _p(dg), _p(db), 0, _p(ws), rows, Cc, dt(xs), dt(dy), _st()), 'ln_bwd')
+    return dxs, dr, dg, db
+
+
+def colsum(a: torch.Tensor, Cc: Optional[int] = None) -> torch.Tensor:
+    """fp32 column sums of a viewed as [rows, C] (bias gradients, batch reductions)."""
+    Cc = Cc or a.shape[-1]
+    rows = a.numel() // Cc
+    out = torch.empty(Cc, device=a.device, dtype=torch.float32)
+    ws = torch.empty(max(1, int(lib().apb_colsum_workspace_floats(rows, Cc))), device=a.device, dtype=torch.float32)
+    check(lib().apb_colsum(_p(a), rows, Cc, _p(out), 0, _p(ws), dt(a), _st()), 'colsum')
+    return out
+
+
+# ------------------------------------------------------------------ GEMM
+EPI_NONE, EPI_GELU, EPI_DGELU, EPI_ACC = 0, 1, 2, 3
+_FORCE_SIMT = False   # tests flip this to run the bf16 model on the CUDA-core GEMM
+
+
+def gemm(a, b, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = False, bias=None, epilogue: int = EPI_NONE,
+         aux=None, out=None, out_dtype=None):
+    """C[M,N] = epi(A(m,k) B(n,k) + bias).  bf16 inputs -> tcgen05 kernel, fp32 inputs -> CUDA-core fp32 kernel."""
+    assert a.dtype == b.dtype, (a.dtype, b.dtype)
+    out_dtype = out_dtype or a.dtype
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    if epilogue == EPI_GELU and aux is None:
+        aux = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    assert a.numel() == M * K and b.numel() == N * K, (a.shape, b.shape, M, N, K)
+    use_tc = a.dtype == torch.bfloat16 and not _FORCE_SIMT and tc_supported(M, N, K)
+    fn = lib().apb_gemm_tc if use_tc else lib().apb_gemm_simt
+    check(fn(_p(a), _p(b), _p(out), _p(bias), _p(aux), M, N, K, int(trans_a), int(trans_b), epilogue, dt(a),
+             _CODES[out_dtype], _st()), 'gemm_tc' if use_tc else 'gemm_simt')
+    return (out, aux) if epilogue == EPI_GELU else out
+
+
+def tc_supported(M: int, N: int, K: int) -> bool:
+    """Shape envelope of the tcgen05 kernel: TMA needs 16-byte aligned row pitches (bf16: multiples of 8)."""
+    return M % 8 == 0 and N % 8 == 0 and K % 8 == 0 and M >= 8 and N >= 8 and K >= 8
+
+
+# ------------------------------------------------------------------ attention cores
+def mhsa_fwd(qkv: torch.Tensor, heads: int, scale: float):
+    B, N, C3 = qkv.shape
+    D = C3 // (3 * heads)
+    out = torch.empty((B, N, heads * D), device=qkv.device, dtype=qkv.dtype)
+    lse = torch.empty((B, heads, N), device=qkv.device, dtype=torch.float32)
+    check(lib().apb_mhsa_fwd(_p(qkv), _p(out), _p(lse), B, N, heads, D, scale, dt(qkv), _st()), 'mhsa_fwd')
+    return out, lse
+
+
+def mhsa_bwd(qkv, out, dout, lse, heads: int, scale: float):
+    B, N, C3 = qkv.shape
+    D = C3 // (3 * heads)
+    dqkv = torch.empty_like(qkv)
+    ws = torch.empty(B * heads * N, device=qkv.device, dtype=torch.float32)
+    check(lib().apb_mhsa_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(dqkv), _p(ws), B, N, heads, D, scale, dt(qkv), _st()),
+          'mhsa_bwd')
+    return dqkv
+
+
+def class_attn_fwd(q, kv, heads: int, scale: float):
+    B, N, C2 = kv.shape
+    D = C2 // (2 * heads)
+    out = torch.empty_like(q)
+    check(lib().apb_class_attn_fwd(_p(q), _p(kv), _p(out), B, N, heads, D, scale, dt(q), _st()), 'class_attn_fwd')
+    return out
+
+
+def class_attn_bwd(q, kv, dout, heads: int, scale: float):
+    B, N, C2 = kv.shape
+    D = C2 // (2 * heads)
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    check(lib().apb_class_attn_bwd(_p(q), _p(kv), _p(dout), _p(dq), _p(dkv), B, N, heads, D, scale, dt(q), _st()),
+          'class_attn_bwd')
+    return dq, dkv
+
+
+# ------------------------------------------------------------------ elementwise / layout
+def avgpool2_fwd(x):
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, (H + 1) // 2, (W + 1) // 2, Cc), device=x.device, dtype=x.dtype)
+    check(lib().apb_avgpool2_fwd(_p(x), _p(y), B, H, W, Cc, dt(x), _st()), 'avgpool2_fwd')
+    return y
+
+
+def avgpool2_bwd(dy, H: int, W: int, accumulate_into=None):
+    B, _, _, Cc = dy.shape
+    dx = accumulate_into if accumulate_into is not None else torch.empty((B, H, W, Cc), device=dy.device, dtype=dy.dtype)
+    check(lib().apb_avgpool2_bwd(_p(dy), _p(dx), B, H, W, Cc, int(accumulate_into is not None), dt(dy), _st()), 'avgpool2_bwd')
+    return dx
+
+
+def flip_in_box(x, box: Sequence[int]):
+    """x [B,H,W,C]; box = (r0, c0, r1, c1) on the (H, W) grid."""
+    B, H, W, Cc = x.shape
+    y = torch.empty_like(x)
+    r0, c0, r1, c1 = [int(b) for b in box]
+    check(lib().apb_flip_in_box(_p(x), _p(y), B, H, W, Cc, r0, c0, r1, c1, dt(x), _st()), 'flip_in_box')
+    return y
+
+
+def patchify(x, p: int):
+    B, H, W, Cc = x.shape
+    rows = torch.empty((B * (H // p) * (W // p), p * p * Cc), device=x.device, dtype=x.dtype)
+    check(lib().apb_patchify(_p(x), _p(rows), B, H, W, Cc, p, dt(x), _st()), 'patchify')
+    return rows
+
+
+def unpatchify(rows, B: int, H: int, W: int, Cc: int, p: int):
+    x = torch.empty((B, H, W, Cc), device=rows.device, dtype=rows.dtype)
+    check(lib().apb_unpatchify(_p(rows), _p(x), B, H, W, Cc, p, dt(rows), _st()), 'unpatchify')
+    return x
+
+
+def bicubic_resize(src, h0: int, w0: int):
+    h, w, Cc = src.shape
+    dst = torch.empty((h0, w0, Cc), device=src.device, dtype=torch.float32)
+    check(lib().apb_bicubic_resize(_p(src), _p(dst), h, w, h0, w0, Cc, _st()), 'bicubic_resize')
+    return dst
+
+
+def bicubic_resize_bwd(ddst, h: int, w: int):
+    h0, w0, Cc = ddst.shape
+    dsrc = torch.empty((h, w, Cc), device=ddst.device, dtype=torch.float32)
+    check(lib().apb_bicubic_resize_bwd(_p(ddst), _p(dsrc), h, w, h0, w0, Cc, _st()), 'bicubic_resize_bwd')
+    return dsrc
+
+
+def add_bcast(x, p, out_dtype=None):
+    """x [B, ...] + p [...] (fp32) broadcast over the batch dim; output dtype may differ from x's."""
+    out_dtype = out_dtype or x.dtype
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    inner = p.numel()
+    check(lib().apb_add_bcast(_p(x), _p(p), _p(out), x.numel() // inner, inner, dt(x), _CODES[out_dtype], _st()), 'add_bcast')
+    return out
+
+
+def scale_cast(x, out_dtype, rs=None):
+    """out[b] = x[b] * rs[b] converted to out_dtype (rs None = plain cast)."""
+    if rs is None and x.dtype == out_dtype:
+        return x
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    batch = x.shape[0] if rs is not None else 1
+    check(lib().apb_scale_cast(_p(x), _p(rs), _p(out), batch, x.numel() // batch, dt(x), _CODES[out_dtype], _st()), 'scale_cast')
+    return out
+
+
+def residual_add(x, r, rs=None, out_dtype=None):
+    """out = x + rs[b] * r  (x: stream dtype, r: compute dtype)."""
+    out_dtype = out_dtype or x.dtype
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    batch = x.shape[0] if rs is not None else 1
+    check(lib().apb_residual_add(_p(x), _p(r), _p(rs), _p(out), batch, x.numel() // batch, dt(x), dt(r), _CODES[out_dtype],
+                                 _st()), 'residual_add')
+    return out
+
+
+def cast(x, dtype):
+    if x.dtype == dtype:
+        return x
+    out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    check(lib().apb_cast(_p(x), _p(out), x.numel(), dt(x), _CODES[dtype], _st()), 'cast')
+    return out
+
+
+def add(a, b):
+    out = torch.empty_like(a)
+    check(lib().apb_add(_p(a), _p(b), _p(out), a.numel(), dt(a), _st()), 'add')
+    return out
+
+
+def gelu_fwd(x):
+    y = torch.empty_like(x)
+    check(lib().apb_gelu_fwd(_p(x), _p(y), x.numel(), dt(x), _st()), 'gelu_fwd')
+    return y
+
+
+def gelu_bwd(x, dy):
+    dx = torch.empty_like(x)
+    check(lib().apb_gelu_bwd(_p(x), _p(dy), _p(dx), x.numel(), dt(x), _st()), 'gelu_bwd')
+    return dx
+
+
+def adamw_ema(p, g, m, v, lr, beta1, beta2, eps, wd, bc1, bc2, emas=(), decays=(), shadow=None):
+    n = p.numel()
+    k = len(emas)
+    ptrs = (C.c_void_p * max(k, 1))(*[e.data_ptr() for e in emas])
+    dec = (C.c_float * max(k, 1))(*[float(d) for d in decays])
+    check(lib().apb_adamw_ema(_p(p), _p(g), _p(m), _p(v), n, lr, beta1, beta2, eps, wd, bc1, bc2,
+                              C.cast(ptrs, C.POINTER(C.c_void_p)), C.cast(dec, C.POINTER(C.c_float)), k, _p(shadow), _st()),
+          'adamw_ema')

@@ -1,0 +1,469 @@
+"""Autograd layer over the C-ABI kernels: per-op Functions plus fused per-block Functions.
+
+dtype policy (the `prog/scaler.py` AMP path, re-targeted at bf16):
+  * parameters, LayerNorm/softmax/loss statistics, optimizer state and the RESIDUAL STREAM are fp32;
+  * under `torch.autocast('cuda', dtype=torch.bfloat16)` (or `autoprog_b200.autocast()`) every GEMM / attention /
+    branch activation is bf16 with fp32 accumulation; without autocast everything is fp32 on the CUDA-core
+    parity kernels (1e-5 mode).
+Backward never consults autocast state: each Function records its compute dtype at forward time.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional
+
+import torch
+
+from . import kernels as K
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def compute_dtype(x: Optional[torch.Tensor] = None) -> torch.dtype:
+    if torch.is_autocast_enabled('cuda') and torch.get_autocast_dtype('cuda') == BF16:
+        return BF16
+    if x is not None and x.dtype == BF16:
+        return BF16
+    return F32
+
+
+class autocast(torch.autocast):
+    """`with autoprog_b200.autocast():` == torch.autocast('cuda', dtype=torch.bfloat16) (drop-in for amp_autocast)."""
+
+    def __init__(self, enabled: bool = True):
+        super().__init__('cuda', dtype=BF16, enabled=enabled)
+
+
+# ---------------------------------------------------------------------------------------------
+# bf16 shadow copies of fp32 parameters, refreshed when the parameter is modified in place
+# ---------------------------------------------------------------------------------------------
+_WCACHE = {}
+
+
+def wcast(p: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    src = p.detach()
+    if not src.is_contiguous():
+        src = src.contiguous()
+    if src.dtype == dtype:
+        return src
+    key = id(p)
+    ent = _WCACHE.get(key)
+    if ent is not None and ent[0] == p._version and ent[1] == p.data_ptr() and ent[2].shape == p.shape:
+        return ent[2]
+    t = K.cast(src, dtype)
+    if ent is None:
+        weakref.finalize(p, _WCACHE.pop, key, None)
+    _WCACHE[key] = (p._version, p.data_ptr(), t)
+    return t
+
+
+def register_shadow(p: torch.Tensor, shadow: torch.Tensor) -> None:
+    """Let a fused optimizer publish the bf16 copy it wrote (skips the cast kernel on the next forward)."""
+    if id(p) not in _WCACHE:
+        weakref.finalize(p, _WCACHE.pop, id(p), None)
+    _WCACHE[id(p)] = (p._version, p.data_ptr(), shadow)
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# raw (non-autograd) linear helpers shared by the Functions
+# ---------------------------------------------------------------------------------------------
+def _lin_fwd(x2d, w, bias, epilogue=K.EPI_NONE):
+    """x2d [M,K] (compute dtype), w [N,K] same dtype, bias fp32 or None."""
+    M, Kd = x2d.shape
+    return K.gemm(x2d, w, M, w.shape[0], Kd, bias=bias, epilogue=epilogue)
+
+
+def _lin_bwd(dy2d, x2d, w, need_dx=True, need_dw=True, need_db=True, dgelu_aux=None):
+    """Returns (dx [M,K] compute dtype, dw [N,K] fp32, db [N] fp32)."""
+    M, N = dy2d.shape
+    Kd = w.shape[1]
+    dx = dw = db = None
+    if need_dx:
+        if dgelu_aux is not None:
+            dx = K.gemm(dy2d, w, M, Kd, N, trans_b=True, epilogue=K.EPI_DGELU, aux=dgelu_aux)
+        else:
+            dx = K.gemm(dy2d, w, M, Kd, N, trans_b=True)
+    if need_dw:
+        dw = K.gemm(dy2d, x2d, N, Kd, M, trans_a=True, trans_b=True, out_dtype=F32)
+    if need_db:
+        db = K.colsum(dy2d, N)
+    return dx, dw, db
+
+
+# ---------------------------------------------------------------------------------------------
+# per-op Functions
+# ---------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b (nn.Linear, e.g. models/volo.py:67-71,156-158,180-182,253-256,547-554)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        cdt = compute_dtype(x)
+        xc = _c(K.cast(_c(x), cdt)).reshape(-1, x.shape[-1])
+        w = wcast(weight, cdt)
+        y = _lin_fwd(xc, w, None if bias is None else bias.detach())
+        ctx.save_for_backward(xc, w)
+        ctx.has_bias = bias is not None
+        ctx.x_dtype = x.dtype
+        ctx.x_shape = x.shape
+        return y.reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, w = ctx.saved_tensors
+        dy2 = _c(K.cast(_c(dy), xc.dtype)).reshape(-1, w.shape[0])
+        dx, dw, db = _lin_bwd(dy2, xc, w, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                              ctx.has_bias and ctx.needs_input_grad[2])
+        if dx is not None:
+            dx = K.cast(dx, ctx.x_dtype).reshape(ctx.x_shape)
+        return dx, dw, db
+
+
+class LayerNormFn(torch.autograd.Function):
+    """y = LN(x) in the compute dtype; x may be the fp32 stream (nn.LayerNorm, models/volo.py:472)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        cdt = compute_dtype(x)
+        xc = _c(x)
+        if xc.dtype == BF16 and cdt == F32:
+            xc = K.cast(xc, F32)
+        _, y, mean, rstd = K.ln_fwd(xc, weight.detach(), bias.detach(), eps, cdt)
+        ctx.save_for_backward(xc, mean, rstd, weight.detach())
+        ctx.x_dtype = x.dtype
+        ctx.cdt = cdt
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, mean, rstd, w = ctx.saved_tensors
+        dyc = K.cast(_c(dy), ctx.cdt)
+        dxs, _, dg, db = K.ln_bwd(dyc, xc, mean, rstd, w)
+        return K.cast(dxs, ctx.x_dtype), dg, db, None
+
+
+class GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        xc = _c(x)
+        ctx.save_for_backward(xc)
+        return K.gelu_fwd(xc)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        return K.gelu_bwd(xc, K.cast(_c(dy), xc.dtype))
+
+
+class OutlookCoreFn(torch.autograd.Function):
+    """unfold -> softmax -> attn@v -> fold as one kernel per direction (models/volo.py:83-98)."""
+
+    @staticmethod
+    def forward(ctx, v, logits, heads, scale, simt=False):
+        v, logits = _c(v), _c(logits)
+        ctx.save_for_backward(v, logits)
+        ctx.cfg = (heads, scale, simt)
+        return K.outlook_fwd(v, logits, heads, scale, simt)
+
+    @staticmethod
+    def backward(ctx, dy):
+        v, logits = ctx.saved_tensors
+        heads, scale, simt = ctx.cfg
+        dv, dl = K.outlook_bwd(v, logits, K.cast(_c(dy), v.dtype), heads, scale, simt)
+        return dv, dl, None, None, None
+
+
+class MhsaCoreFn(torch.autograd.Function):
+    """softmax(q k^T scale) v on packed qkv [B,N,3C] (models/volo.py:188-197)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, scale):
+        qkv = _c(qkv)
+        out, lse = K.mhsa_fwd(qkv, heads, scale)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.cfg = (heads, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        heads, scale = ctx.cfg
+        return K.mhsa_bwd(qkv, out, K.cast(_c(dout), qkv.dtype), lse, heads, scale), None, None
+
+
+class ClassAttnCoreFn(torch.autograd.Function):
+    """cls-query attention (models/volo.py:264-275): q [B,C], kv [B,N,2C] -> [B,C]."""
+
+    @staticmethod
+    def forward(ctx, q, kv, heads, scale):
+        q, kv = _c(q), _c(kv)
+        ctx.save_for_backward(q, kv)
+        ctx.cfg = (heads, scale)
+        return K.class_attn_fwd(q, kv, heads, scale)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, kv = ctx.saved_tensors
+        heads, scale = ctx.cfg
+        dq, dkv = K.class_attn_bwd(q, kv, K.cast(_c(dout), q.dtype), heads, scale)
+        return dq, dkv, None, None
+
+
+class AvgPool2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.hw = (x.shape[1], x.shape[2])
+        return K.avgpool2_fwd(_c(x))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.avgpool2_bwd(_c(dy), *ctx.hw)
+
+
+class FlipInBoxFn(torch.autograd.Function):
+    """mix-token / un-mix (models/volo.py:655-658, 687-689); self-inverse permutation."""
+
+    @staticmethod
+    def forward(ctx, x, box):
+        ctx.box = tuple(int(b) for b in box)
+        return K.flip_in_box(_c(x), ctx.box)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.flip_in_box(_c(dy), ctx.box), None
+
+
+class PatchConvFn(torch.autograd.Function):
+    """Conv2d(kernel=p, stride=p) on an NHWC tensor as patchify + GEMM (models/volo.py:370-373, 389)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, p):
+        cdt = compute_dtype(x)
+        B, H, W, Cin = x.shape
+        xc = K.cast(_c(x), cdt)
+        rows = K.patchify(xc, p)
+        # conv weight [Cout, Cin, p, p] -> GEMM weight [Cout, (kh, kw, cin)]
+        w2 = wcast_conv(weight, cdt)
+        y = _lin_fwd(rows, w2, None if bias is None else bias.detach())
+        ctx.save_for_backward(rows, w2)
+        ctx.meta = (B, H, W, Cin, p, x.dtype, weight.shape, bias is not None)
+        return y.reshape(B, H // p, W // p, weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        rows, w2 = ctx.saved_tensors
+        B, H, W, Cin, p, xdt, wshape, has_bias = ctx.meta
+        dy2 = K.cast(_c(dy), rows.dtype).reshape(-1, wshape[0])
+        drows, dw2, db = _lin_bwd(dy2, rows, w2, ctx.needs_input_grad[0], True, has_bias)
+        dx = None
+        if drows is not None:
+            dx = K.cast(K.unpatchify(drows, B, H, W, Cin, p), xdt)
+        dw = dw2.reshape(wshape[0], p, p, Cin).permute(0, 3, 1, 2).contiguous()
+        return dx, dw, db, None
+
+
+_CONVW = {}
+
+
+def wcast_conv(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """[Cout,Cin,p,p] conv weight -> cached [Cout, p*p*Cin] GEMM weight in K order (kh,kw,cin)."""
+    key = id(weight)
+    ent = _CONVW.get(key)
+    if ent is not None and ent[0] == weight._version and ent[1] == weight.data_ptr() and ent[3] == dtype:
+        return ent[2]
+    co = weight.shape[0]
+    w2 = K.cast(weight.detach().permute(0, 2, 3, 1).reshape(co, -1).contiguous(), dtype)
+    if ent is None:
+        weakref.finalize(weight, _CONVW.pop, key, None)
+    _CONVW[key] = (weight._version, weight.data_ptr(), w2, dtype)
+    return w2
+
+
+class PosEmbedAddFn(torch.autograd.Function):
+    """x + bicubic_resize(pos_embed) (models/volo.py:580-596, 627-628); output joins the fp32 residual stream."""
+
+    @staticmethod
+    def forward(ctx, x, pos):
+        B, h0, w0, Cc = x.shape
+        _, h, w, _ = pos.shape
+        p = pos.detach().reshape(h, w, Cc)
+        p = _c(p) if (h == h0 and w == w0) else K.bicubic_resize(_c(p), h0, w0)
+        ctx.meta = (h, w, h0, w0, Cc, x.dtype)
+        out_dtype = F32 if x.dtype in (F32, BF16) else x.dtype
+        return K.add_bcast(_c(x), p, out_dtype=out_dtype)
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, w, h0, w0, Cc, xdt = ctx.meta
+        d = _c(dout)
+        dp = K.colsum(d, h0 * w0 * Cc).reshape(h0, w0, Cc)
+        if not (h == h0 and w == w0):
+            dp = K.bicubic_resize_bwd(dp, h, w)
+        return K.cast(d, xdt), dp.reshape(1, h, w, Cc)
+
+
+class CastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src = x.dtype
+        return K.cast(_c(x), dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.cast(_c(dy), ctx.src), None
+
+
+class ResidualAddFn(torch.autograd.Function):
+    """out = x + rs[b] * r : x fp32 stream, r compute dtype (DropPath scale rs optional, not differentiated)."""
+
+    @staticmethod
+    def forward(ctx, x, r, rs, out_dtype):
+        ctx.meta = (x.dtype, r.dtype)
+        ctx.rs = rs
+        return K.residual_add(_c(x), _c(r), rs, out_dtype)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xdt, rdt = ctx.meta
+        d = _c(dout)
+        return K.scale_cast(d, xdt), K.scale_cast(d, rdt, ctx.rs), None, None
+
+
+class TokenLabelCEFn(torch.autograd.Function):
+    """Fused TokenLabelCrossEntropy forward+gradient (loss/cross_entropy.py:136-156)."""
+
+    @staticmethod
+    def forward(ctx, x_cls, x_aux, target, box_area, w_cls, w_dense):
+        loss, d_cls, d_aux = K.tlce_fwd_bwd(_c(x_cls), _c(x_aux), _c(target), box_area, w_cls, w_dense)
+        ctx.save_for_backward(d_cls, d_aux)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        d_cls, d_aux = ctx.saved_tensors
+        return K.scale_by_scalar(d_cls, g), K.scale_by_scalar(d_aux, g), None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------
+# fused block Functions: one autograd node per Outlooker / Transformer block.
+#
+# The residual stream is carried as (x, r, rs): x fp32, r = the previous block's MLP output still pending
+# (compute dtype), rs = its per-sample DropPath scale.  A block's first LayerNorm kernel performs
+# xs = x + rs*r, so no residual add ever runs as its own pass.
+# ---------------------------------------------------------------------------------------------
+def _flat(t):
+    return t.reshape(-1, t.shape[-1])
+
+
+class _BlockBase(torch.autograd.Function):
+    @staticmethod
+    def _mlp_fwd(n2, w1, b1, w2, b2):
+        u_h = K.gemm(n2, w1, n2.shape[0], w1.shape[0], n2.shape[1], bias=b1, epilogue=K.EPI_GELU)
+        hdn, u = u_h
+        z = K.gemm(hdn, w2, hdn.shape[0], w2.shape[0], hdn.shape[1], bias=b2)
+        return u, hdn, z
+
+    @staticmethod
+    def _mlp_bwd(dz, n2, u, hdn, w1, w2):
+        du, dw2, db2 = _lin_bwd(dz, hdn, w2, dgelu_aux=u)
+        dn2, dw1, db1 = _lin_bwd(du, n2, w1)
+        return dn2, dw1, db1, dw2, db2
+
+
+class OutlookerFn(_BlockBase):
+    """Outlooker.forward (models/volo.py:140-144) with OutlookAttention.forward (:77-103) and Mlp.forward (:161-167)."""
+
+    @staticmethod
+    def forward(ctx, x, r_in, rs_in, rs_blk, heads, eps, n1w, n1b, wv, wa, ba, wp, bp, n2w, n2b, w1, b1, w2, b2):
+        cdt = compute_dtype()
+        B, H, W, Cc = x.shape
+        rps = H * W
+        scale = (Cc // heads) ** -0.5
+        xs, n1, mu1, rstd1 = K.ln_fwd(_c(x), n1w.detach(), n1b.detach(), eps, cdt, r=None if r_in is None else _c(r_in),
+                                      rs=rs_in, rows_per_sample=rps)
+        xs = xs if xs is not None else _c(x)
+        cv, ca, cp, c1, c2 = (wcast(t, cdt) for t in (wv, wa, wp, w1, w2))
+        n1f = _flat(n1)
+        v = _lin_fwd(n1f, cv, None).reshape(B, H, W, Cc)
+        pooled = K.avgpool2_fwd(n1)
+        lg = _lin_fwd(_flat(pooled), ca, ba.detach()).reshape(B, pooled.shape[1], pooled.shape[2], -1)
+        y = K.outlook_fwd(v, lg, heads, scale)
+        o = _lin_fwd(_flat(y), cp, bp.detach()).reshape(B, H, W, Cc)
+        x1, n2, mu2, rstd2 = K.ln_fwd(xs, n2w.detach(), n2b.detach(), eps, cdt, r=o, rs=rs_blk, rows_per_sample=rps)
+        n2f = _flat(n2)
+        u, hdn, z = _BlockBase._mlp_fwd(n2f, c1, b1.detach(), c2, b2.detach())
+        ctx.save_for_backward(xs, mu1, rstd1, n1, v, pooled, lg, y, x1, mu2, rstd2, n2, u, hdn, cv, ca, cp, c1, c2,
+                              n1w.detach(), n2w.detach(), rs_in if rs_in is not None else x.new_empty(0),
+                              rs_blk if rs_blk is not None else x.new_empty(0))
+        ctx.meta = (heads, scale, r_in is not None, rs_in is not None, rs_blk is not None)
+        return x1, z.reshape(B, H, W, Cc)
+
+    @staticmethod
+    def backward(ctx, dx1_out, dz):
+        (xs, mu1, rstd1, n1, v, pooled, lg, y, x1, mu2, rstd2, n2, u, hdn, cv, ca, cp, c1, c2, n1w, n2w, rs_in,
+         rs_blk) = ctx.saved_tensors
+        heads, scale, has_r, has_rs_in, has_rs_blk = ctx.meta
+        B, H, W, Cc = xs.shape
+        rps = H * W
+        cdt = n1.dtype
+        dz2 = _flat(K.cast(_c(dz), cdt))
+        dn2, dw1, db1, dw2, db2 = _BlockBase._mlp_bwd(dz2, _flat(n2), u, hdn, c1, c2)
+        dx1, do, dn2w, dn2b = K.ln_bwd(dn2.reshape(xs.shape), x1, mu2, rstd2, n2w, dres=_c(dx1_out), want_dr=True,
+                                       rs=rs_blk if has_rs_blk else None, rows_per_sample=rps)
+        do2 = _flat(do)
+        dy, dwp, dbp = _lin_bwd(do2, _flat(y), cp)
+        dv, dlg = K.outlook_bwd(v, lg, dy.reshape(xs.shape), heads, scale)
+        dn1, dwv, _ = _lin_bwd(_flat(dv), _flat(n1), cv, need_db=False)
+        dpooled, dwa, dba = _lin_bwd(_flat(dlg), _flat(pooled), ca)
+        dn1 = K.avgpool2_bwd(dpooled.reshape(pooled.shape), H, W, accumulate_into=dn1.reshape(xs.shape))
+        dxs, dr, dn1w, dn1b = K.ln_bwd(dn1, xs, mu1, rstd1, n1w, dres=dx1, want_dr=has_r,
+                                       rs=rs_in if has_rs_in else None, rows_per_sample=rps)
+        return (dxs, dr, None, None, None, None, dn1w, dn1b, dwv, dwa, dba, dwp, dbp, dn2w, dn2b, dw1, db1, dw2, db2)
+
+
+class TransformerFn(_BlockBase):
+    """Transformer.forward (models/volo.py:230-234) with Attention.forward (:185-201) and Mlp.forward (:161-167)."""
+
+    @staticmethod
+    def forward(ctx, x, r_in, rs_in, rs_blk, heads, eps, n1w, n1b, wqkv, bqkv, wp, bp, n2w, n2b, w1, b1, w2, b2):
+        cdt = compute_dtype()
+        shp = x.shape
+        Cc = shp[-1]
+        B = shp[0]
+        N = x.numel() // (B * Cc)
+        scale = (Cc // heads) ** -0.5
+        xs, n1, mu1, rstd1 = K.ln_fwd(_c(x), n1w.detach(), n1b.detach(), eps, cdt, r=None if r_in is None else _c(r_in),
+                                      rs=rs_in, rows_per_sample=N)
+        xs = xs if xs is not None else _c(x)
+        cqkv, cp, c1, c2 = (wcast(t, cdt) for t in (wqkv, wp, w1, w2))
+        qkv = _lin_fwd(_flat(n1), cqkv, None if bqkv is None else bqkv.detach()).reshape(B, N, 3 * Cc)
+        a, lse = K.mhsa_fwd(qkv, heads, scale)
+        o = _lin_fwd(_flat(a), cp, bp.detach()).reshape(shp)
+        x1, n2, mu2, rstd2 = K.ln_fwd(xs, n2w.detach(), n2b.detach(), eps, cdt, r=o, rs=rs_blk, rows_per_sample=N)
+        u, hdn, z = _BlockBase._mlp_fwd(_flat(n2), c1, b1.detach(), c2, b2.detach())
+        ctx.save_for_backward(xs, mu1, rstd1, n1, qkv, a, lse, x1, mu2, rstd2, n2, u, hdn, cqkv, cp, c1, c2,
+                              n1w.detach(), n2w.detach(), rs_in if rs_in is not None else x.new_empty(0),
+                              rs_blk if rs_blk is not None else x.new_empty(0))
+        ctx.meta = (heads, scale, r_in is not None, rs_in is not None, rs_blk is not None, bqkv is not None, N)
+        return x1, z.reshape(shp)
+
+    @staticmethod
+    def backward(ctx, dx1_out, dz):
+        (xs, mu1, rstd1, n1, qkv, a, lse, x1, mu2, rstd2, n2, u, hdn, cqkv, cp, c1, c2, n1w, n2w, rs_in,
+         rs_blk) = ctx.saved_tensors
+        heads, scale, has_r, has_rs_in, has_rs_blk, has_bqkv, N = ctx.meta
+        cdt = n1.dtype
+        dz2 = _flat(K.cast(_c(dz), cdt))
+        dn2, dw1, db1, dw2, db2 = _BlockBase._mlp_bwd(dz2, _flat(n2), u, hdn, c1, c2)
+        dx1, do, dn2w, dn2b = K.ln_bwd(dn2.reshape(xs.shape), x1, mu2, rstd2, n2w, dres=_c(dx1_out), want_dr=True,
+                                       rs=rs_blk if has_rs_blk else None, rows_per_sample=N)
+        da, dwp, dbp = _lin_bwd(_flat(do), _flat(a), cp)
+        dqkv = K.mhsa_bwd(qkv, a, da.reshape(a.shape), lse, heads, scale)
+        dn1, dwqkv, dbqkv = _lin_bwd(_flat(dqkv), _flat(n1), cqkv, need_db=has_bqkv)
+        dxs, dr, dn1w, dn1b = K.ln_bwd(dn1.reshape(xs.shape), xs, mu1, rstd1, n1w, dres=dx1, want_dr=has_r,
+                                       rs=rs_in if has_rs_in else None, rows_per_sample=N)
+        return (dxs, dr, None, None, None, None, dn1w, dn1b, dwqkv, dbqkv, dwp, dbp, dn2w, dn2b, dw1, db1, dw2, db2)

@@ -1,0 +1,140 @@
+/* autoprog_b200 C ABI — the drop-in boundary of the B200-native AutoProg hot path.
+ *
+ * The reference (changlin31/AutoProg) has no FFI of its own: its hot path is `nn.Module.forward` calling
+ * ATen ops.  Each entry point below is what a Python binding for that path binds instead
+ * of the ATen call chain it names (file:line in /root/reference).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain C: device pointers + sizes, `apb_stream_t` is a `cudaStream_t` passed as `void*`;
+ *   - every tensor is contiguous in the documented layout; the CALLER allocates outputs and workspaces
+ *     (PyTorch's caching allocator in the shipped binding); kernels never allocate, free or synchronise;
+ *   - dtype codes: APB_F32 = 0, APB_BF16 = 1 (activations); parameters / statistics / loss are fp32;
+ *   - return value: 0 = ok, > 0 = cudaError_t of the failed launch, < 0 = argument check
+ *     (-1 arg, -2 dtype, -3 shape, -4 unsupported); `apb_last_error()` has the message (thread-local);
+ *   - thread-safe: no mutable global state except a mutex-guarded TMA-descriptor cache; all work is
+ *     enqueued on the given stream (CUDA-graph capturable).
+ */
+#ifndef AUTOPROG_B200_H_
+#define AUTOPROG_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* apb_stream_t;
+
+#define APB_F32 0
+#define APB_BF16 1
+
+const char* apb_last_error(void);
+int apb_abi_version(void);
+
+/* ---- OutlookAttention core: nn.Unfold -> softmax(scale*logits) -> attn@v -> F.fold  (models/volo.py:83-98)
+ * v,y,dy,dv [B,H,W,heads*32] NHWC; logits,dlogits [B,ceil(H/2),ceil(W/2),heads*81] (pre-scale output of the
+ * `attn` Linear, channel = head*81 + P*9 + Q).  kernel 3, padding 1, stride 2, head_dim 32 (every VOLO variant).
+ * `_simt` = fp32-exact CUDA-core path (parity mode); the un-suffixed entry picks the tensor-core bf16 kernel
+ * for APB_BF16 and the SIMT kernel for APB_F32. */
+int apb_outlook_fwd_simt(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale,
+                         int dtype, apb_stream_t stream);
+int apb_outlook_bwd_simt(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H,
+                         int W, int heads, float scale, int dtype, apb_stream_t stream);
+int apb_outlook_fwd(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int dtype,
+                    apb_stream_t stream);
+int apb_outlook_bwd(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
+                    int heads, float scale, int dtype, apb_stream_t stream);
+
+/* ---- TokenLabelCrossEntropy forward + gradient in one pass  (loss/cross_entropy.py:136-156, :30-36)
+ * x_cls [B,C], x_aux [B,N,C] (dtype); target fp32 [B,C,2+N] (target_is_3d=1) or [B,C] (0);
+ * box_area = (bbx2-bbx1)*(bby2-bby1); loss: 1 float; d_cls/d_aux: gradients for upstream gradient 1.
+ * workspace: apb_tlce_workspace_floats(B,N) floats. */
+long long apb_tlce_workspace_floats(int B, int N);
+int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, int target_is_3d, int B, int N, int C,
+                     int box_area, float w_cls, float w_dense, float* loss, void* d_cls, void* d_aux, float* workspace,
+                     int dtype, apb_stream_t stream);
+int apb_scale_by_scalar(const void* in, void* out, long long n, const float* scalar, int dtype, apb_stream_t stream);
+
+/* ---- fused residual add (+DropPath per-sample scale) + LayerNorm  (models/volo.py:142-143, 232-233, 306-307)
+ * xs = x + rs[row / rows_per_sample] * r (r, rs, xs_out optional);  y = LN(xs) * gamma + beta (y optional).
+ * bwd: dxs = dres + LN'(dy) (dres optional); dr = rs[b]*dxs (optional, compute dtype: gradient of the branch r).
+ * sdtype: dtype of x/xs_out/dres/dxs (residual stream); cdtype: dtype of r/y/dy/dr. gamma,beta,mean,rstd fp32. */
+int apb_ln_fwd(const void* x, const void* r, const float* rs, int rows_per_sample, const float* gamma, const float* beta,
+               void* xs_out, void* y, float* mean, float* rstd, long long rows, int C, float eps, int sdtype, int cdtype,
+               apb_stream_t stream);
+long long apb_ln_bwd_workspace_floats(int C);
+int apb_ln_bwd(const void* dy, const void* xs, const float* mean, const float* rstd, const float* gamma, const void* dres,
+               void* dxs, void* dr, const float* rs, int rows_per_sample, float* dgamma, float* dbeta, int accumulate,
+               float* workspace, long long rows, int C, int sdtype, int cdtype, apb_stream_t stream);
+long long apb_colsum_workspace_floats(long long rows, int C);
+int apb_colsum(const void* a, long long rows, int C, float* out, int accumulate, float* workspace, int dtype,
+               apb_stream_t stream);
+
+/* ---- GEMM  C[M,N] = epi( sum_k A(m,k) * B(n,k) (+ bias[n]) )   (nn.Linear / patchify convs: models/volo.py:80,88,100,
+ * 161-167,188,199,253-254,370-373,389; fwd = NT, dgrad = NN, wgrad = TN via the transpose flags)
+ *   trans_a = 0: A stored [M,K] row-major; 1: A stored [K,M] row-major.
+ *   trans_b = 0: B stored [N,K] row-major (nn.Linear weight); 1: B stored [K,N] row-major.
+ *   epilogue: 0 none | 1 GELU: aux = acc+bias (pre-activation, out dtype), C = gelu(aux)
+ *             | 2 dGELU: C = acc * gelu'(aux)  | 3 accumulate: C += acc (out fp32 only)
+ *   in_dtype: dtype of A and B; out_dtype: dtype of C/aux; bias fp32 or NULL.
+ * apb_gemm_simt: CUDA-core fp32-accumulate path (exact fp32 products; parity mode, any shape).
+ * apb_gemm_tc  : tcgen05/TMEM/TMA bf16 path (in_dtype must be APB_BF16; K % 8 == 0 etc.). */
+int apb_gemm_simt(const void* A, const void* B, void* C, const float* bias, void* aux, int M, int N, int K, int trans_a,
+                  int trans_b, int epilogue, int in_dtype, int out_dtype, apb_stream_t stream);
+int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* aux, int M, int N, int K, int trans_a,
+                int trans_b, int epilogue, int in_dtype, int out_dtype, apb_stream_t stream);
+
+/* ---- multi-head self-attention core  softmax(q k^T * scale) v  (models/volo.py:188-197)
+ * qkv [B,N,3*heads*D] laid out (3, heads, D) per token; out [B,N,heads*D]; lse [B,heads,N] fp32 (saved for bwd).
+ * bwd: dqkv same layout as qkv; workspace: B*heads*N floats (row dots D_i). */
+int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, int dtype,
+                 apb_stream_t stream);
+int apb_mhsa_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
+                 int B, int N, int heads, int D, float scale, int dtype, apb_stream_t stream);
+
+/* ---- class attention core (cls query vs all tokens)  (models/volo.py:264-275)
+ * q [B,heads*D]; kv [B,N,2*heads*D] laid out (2, heads, D); out [B,heads*D]. */
+int apb_class_attn_fwd(const void* q, const void* kv, void* out, int B, int N, int heads, int D, float scale, int dtype,
+                       apb_stream_t stream);
+int apb_class_attn_bwd(const void* q, const void* kv, const void* dout, void* dq, void* dkv, int B, int N, int heads,
+                       int D, float scale, int dtype, apb_stream_t stream);
+
+/* ---- elementwise / layout kernels
+ * avgpool2: AvgPool2d(2,2,ceil_mode=True) on NHWC (models/volo.py:75,87) and its transpose.
+ * flip_in_box: mix-token / un-mix (models/volo.py:655-658, 687-689): inside rows [r0,r1) x cols [c0,c1) of the
+ *   [B,H,W,C] grid take sample B-1-b; self-inverse, so the backward is the same call on the gradient.
+ * patchify: NHWC [B,H,W,C] -> rows [B*(H/p)*(W/p), p*p*C] with K order (kh,kw,c) (conv p x p stride p as a GEMM,
+ *   models/volo.py:370-373, 389); unpatchify is the inverse permutation.
+ * bicubic_resize: pos-embed resize (models/volo.py:580-596): src fp32 [h,w,C] -> dst fp32 [h0,w0,C],
+ *   scale_factor=(h0+0.1)/h semantics, A=-0.75; bicubic_resize_bwd is its transpose (dst grad -> src grad).
+ * add_bcast: out[b,i] = x[b,i] + p[i] (pos-embed broadcast add, in/out dtypes may differ).  cast: dtype conversion. */
+int apb_avgpool2_fwd(const void* x, void* y, int B, int H, int W, int C, int dtype, apb_stream_t stream);
+int apb_avgpool2_bwd(const void* dy, void* dx, int B, int H, int W, int C, int accumulate, int dtype, apb_stream_t stream);
+int apb_flip_in_box(const void* x, void* y, int B, int H, int W, int C, int r0, int c0, int r1, int c1, int dtype,
+                    apb_stream_t stream);
+int apb_patchify(const void* x, void* rows, int B, int H, int W, int C, int p, int dtype, apb_stream_t stream);
+int apb_unpatchify(const void* rows, void* x, int B, int H, int W, int C, int p, int dtype, apb_stream_t stream);
+int apb_bicubic_resize(const float* src, float* dst, int h, int w, int h0, int w0, int C, apb_stream_t stream);
+int apb_bicubic_resize_bwd(const float* ddst, float* dsrc, int h, int w, int h0, int w0, int C, apb_stream_t stream);
+int apb_add_bcast(const void* x, const float* p, void* out, long long batch, long long inner, int in_dtype,
+                  int out_dtype, apb_stream_t stream);
+int apb_cast(const void* in, void* out, long long n, int in_dtype, int out_dtype, apb_stream_t stream);
+/* out[b,i] = in[b,i] * rs[b] (rs NULL = 1) with dtype conversion; residual_add: out = x + rs[b]*r. */
+int apb_scale_cast(const void* in, const float* rs, void* out, long long batch, long long inner, int in_dtype,
+                   int out_dtype, apb_stream_t stream);
+int apb_residual_add(const void* x, const void* r, const float* rs, void* out, long long batch, long long inner,
+                     int x_dtype, int r_dtype, int out_dtype, apb_stream_t stream);
+int apb_add(const void* a, const void* b, void* out, long long n, int dtype, apb_stream_t stream);
+int apb_gelu_fwd(const void* x, void* y, long long n, int dtype, apb_stream_t stream);
+int apb_gelu_bwd(const void* x, const void* dy, void* dx, long long n, int dtype, apb_stream_t stream);
+
+/* ---- fused AdamW + k EMA updates + bf16 shadow weights in one pass over the parameters
+ * (timm create_optimizer('adamw') + 4 x ModelEmaV2.update, main_prog.py:1019-1033)
+ * p,g,m,v fp32 [n]; ema: array (device) of n_ema fp32 pointers, decay: host array of n_ema floats (<= 8);
+ * shadow: optional bf16 copy of the updated parameters (NULL to skip). */
+int apb_adamw_ema(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float bias_corr1, float bias_corr2, float* const* ema_ptrs_host,
+                  const float* decay_host, int n_ema, void* shadow_bf16, apb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUTOPROG_B200_H_ */

@@ -196,6 +196,14 @@ def gen_tables():
         m.set_sample_config({'layer_num': cur, 'min_layer_num': 9, 'max_layer_num': 18})
         flags[str(cur)] = [[i for i, b in enumerate(m.network[s]) if b.is_identity_layer] for s in (0, 2)]
     tab['identity_flags_9_18'] = flags
+    # module tree / state_dict contract
+    import models.submodels as RS
+    ref = RV.volo_d1(img_size=224)
+    tab['state_dict_volo_d1'] = {k: list(v.shape) for k, v in ref.state_dict().items()}
+    tab['modules_volo_d1'] = {n: type(m).__name__ for n, m in ref.named_modules()}
+    ref = RS.model_variant(variant='volo_h12_l18', img_size=224, drop_path_rate=0.1)
+    tab['state_dict_volo_h12_l18'] = {k: list(v.shape) for k, v in ref.state_dict().items()}
+    tab['drop_path_volo_h12_l18'] = {n: m.drop_prob for n, m in ref.named_modules() if type(m).__name__ == 'DropPath'}
     json.dump(tab, open(os.path.join(OUT, 'tables.json'), 'w'), indent=1)
 
 
