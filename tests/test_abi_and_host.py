@@ -1,0 +1,129 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol of include/autoprog_b200.h (no compute calls),
+and the host logic (schedule, layer maps, registry, module tree) matches fixtures produced by the reference."""
+import ctypes
+import json
+import os
+import re
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+import autoprog_b200 as A
+from autoprog_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, 'tests', 'golden')
+TAB = json.load(open(os.path.join(G, 'tables.json')))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, 'include', 'autoprog_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(apb_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), 'run `python -m autoprog_b200.build` (or __graft_entry__.build()) first'
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(lib, s), f'{s} declared in the header but not exported'
+    assert set(_lib.SIGNATURES) == set(syms), set(_lib.SIGNATURES) ^ set(syms)
+    assert _lib.lib().apb_abi_version() == 1
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, 'autoprog_b200')
+    for f in os.listdir(pkg):
+        if f.endswith('.py'):
+            txt = open(os.path.join(pkg, f)).read()
+            assert 'import oracle' not in txt and 'from oracle' not in txt, f
+
+
+def test_cpu_tensors_fail_loudly():
+    m = A.create_model('model_variant', variant='volo_h2_l4', img_size=64, num_classes=10)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        m(torch.randn(1, 3, 64, 64))
+    with pytest.raises(RuntimeError):
+        A.TokenLabelCrossEntropy()((torch.randn(2, 4), torch.randn(2, 3, 4), (0, 0, 0, 0)), torch.rand(2, 4, 5))
+
+
+def test_progressive_schedule_tables():
+    args = SimpleNamespace(num_stages=4, r_scale=0.5, h_scale=1., l_scale=0.5, aa_scale=0.5, dp_scale=0., re_scale=0.,
+                           resize_scale=[1., 1.], aa='rand-m9-mstd0.5-inc1', drop_path=0.1, reprob=0.25,
+                           scale=[0.08, 1.0], epochs=100)
+    t = TAB['train_autoprog_sh']
+    e, r, h, l, aa, dp, re_, rs = A.progressive_schedule(args, r_max=224, h_max=12, l_max=18)
+    assert (e, r, h, l, aa, rs) == (t['e'], t['r'], t['h'], t['l'], t['aa'], t['resize'])
+    assert dp == pytest.approx(t['dp']) and re_ == pytest.approx(t['re'])
+    args2 = SimpleNamespace(**{**vars(args), 'num_stages': 3, 'r_scale': 0.4, 'l_scale': 0.34, 'dp_scale': -0.5,
+                               're_scale': -0.5, 'epochs': 300, 'aa_scale': 0.})
+    t = TAB['alt']
+    e, r, h, l, aa, dp, re_, rs = A.progressive_schedule(args2, r_max=384, h_max=16, l_max=24)
+    assert (e, r, h, l, aa) == (t['e'], t['r'], t['h'], t['l'], t['aa'])
+    assert dp == pytest.approx(t['dp']) and re_ == pytest.approx(t['re'])
+    for v, d, want in TAB['make_divisible']:
+        assert A.make_divisible(v, d) == want
+
+
+def test_layer_index_maps():
+    for key, want in TAB['new_idx'].items():
+        p, n = map(int, key.split('->'))
+        assert [A.new_idx(i, p, n) for i in range(n)] == want
+        assert A.get_new_layer_idx(p, n) == TAB['new_layer_idx'][key]
+
+
+def test_set_sample_config_identity_flags():
+    for cur, want in TAB['identity_flags_9_18'].items():
+        m = A.VOLO([4, 14, 0, 0], img_size=32, num_classes=2, stem_hidden_dim=4, embed_dims=[32, 32, 32, 32],
+                   num_heads=[1, 1, 1, 1], mlp_ratios=[1, 1, 1, 1], downsamples=[True, False, False, False],
+                   outlook_attention=[True, False, False, False], post_layers=['ca', 'ca'])
+        m.set_sample_config({'layer_num': int(cur), 'min_layer_num': 9, 'max_layer_num': 18})
+        got = [[i for i, b in enumerate(m.network[s]) if b.is_identity_layer] for s in (0, 2)]
+        assert got == want
+
+
+def test_module_tree_matches_reference():
+    m = A.create_model('volo_d1', img_size=224)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == TAB['state_dict_volo_d1']
+    assert list(m.state_dict().keys()) == list(TAB['state_dict_volo_d1'].keys())
+    import torch.nn as nn
+    base = {'Linear': nn.Linear, 'LayerNorm': nn.LayerNorm, 'Conv2d': nn.Conv2d, 'BatchNorm2d': nn.BatchNorm2d,
+            'Sequential': nn.Sequential, 'ModuleList': nn.ModuleList}
+    mods = dict(m.named_modules())
+    for name, tname in TAB['modules_volo_d1'].items():
+        assert name in mods, name
+        if tname in base:   # prog/helpers.py dispatches on these container types (isinstance)
+            assert isinstance(mods[name], base[tname]), (name, tname)
+        elif tname not in ('Dropout', 'Identity', 'GELU', 'ReLU', 'Unfold', 'AvgPool2d'):
+            assert type(mods[name]).__name__ == tname, (name, tname)
+    assert len(m.network) == 5 and len(m.network[0]) == 4
+    assert m.no_weight_decay() == {'pos_embed', 'cls_token'}
+    assert m.num_classes == 1000 and m.mix_token and m.pooling_scale == 2 and m.beta == 1.0
+    assert m.default_cfg['crop_pct'] == 0.96 and m.get_classifier() is m.head
+
+
+def test_model_variant_any_size_and_drop_path_rates():
+    m = A.create_model('model_variant', variant='volo_h12_l18', img_size=224, drop_path_rate=0.1, drop_rate=None)
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == TAB['state_dict_volo_h12_l18']
+    got = {n: mod.drop_prob for n, mod in m.named_modules() if type(mod).__name__ == 'DropPath'}
+    want = TAB['drop_path_volo_h12_l18']
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k] == pytest.approx(want[k])
+    n = {l: sum(p.numel() for p in A.create_model('model_variant', variant=f'volo_h12_l{l}').parameters())
+         for l in (9, 18)}
+    assert n[18] == 26632040 and n[9] < n[18]
+    import copy
+    copy.deepcopy(m)   # ModelEmaV2 relies on deepcopy
+
+
+def test_registry_kwarg_filtering():
+    m = A.create_model('volo_d1', pretrained=False, num_classes=10, drop_rate=None, drop_connect_rate=0.2,
+                       drop_path_rate=None, bn_tf=False, bn_momentum=None, bn_eps=None, img_size=64)
+    assert m.head.out_features == 10 and m.pos_embed.shape == (1, 4, 4, 384)
+    assert any(getattr(mod, 'drop_prob', 0) > 0 for mod in m.modules())
+    with pytest.raises(RuntimeError):
+        A.create_model('nope')

@@ -1,0 +1,305 @@
+"""GPU parity tests: every C-ABI kernel against the CPU oracle (oracle/volo_cpu.py) on the same seeded inputs.
+Bar: 1e-5 relative (norm-wise) in fp32, 2e-2 in bf16 against the fp64 oracle (BASELINE.json north_star)."""
+import math
+import os
+
+import pytest
+import torch
+
+from oracle import volo_cpu as O
+from autoprog_b200 import kernels as K
+from gpu_util import G, need_gpu, rel, tol
+
+pytestmark = pytest.mark.gpu
+DT = [torch.float32, torch.bfloat16]
+
+
+def q(t, dtype):
+    """round-trip through dtype so oracle and kernel see identical inputs"""
+    return t.to(dtype).double()
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('simt', [True, False])
+@pytest.mark.parametrize('shape', [(2, 8, 8, 2), (2, 9, 7, 3), (1, 15, 13, 1), (3, 28, 28, 6), (1, 5, 6, 2), (2, 1, 1, 1),
+                                   (1, 2, 3, 1)])
+def test_outlook_core(shape, dtype, simt):
+    dev = need_gpu()
+    B, H, W, heads = shape
+    torch.manual_seed(sum(shape))
+    h, w = (H + 1) // 2, (W + 1) // 2
+    v = q(torch.randn(B, H, W, heads * 32), dtype)
+    lg = q(torch.randn(B, h, w, heads * 81) * 3, dtype)
+    dy = q(torch.randn(B, H, W, heads * 32), dtype)
+    scale = 32 ** -0.5
+    y_ref = O.outlook_core(v, lg, heads, scale)
+    dv_ref, dl_ref = O.outlook_core_bwd(v, lg, dy, heads, scale)
+    vd, lgd, dyd = (t.to(dev, dtype) for t in (v, lg, dy))
+    y = K.outlook_fwd(vd, lgd, heads, scale, simt=simt)
+    dv, dl = K.outlook_bwd(vd, lgd, dyd, heads, scale, simt=simt)
+    t = tol(dtype)
+    assert rel(y, y_ref) < t and rel(dv, dv_ref) < t and rel(dl, dl_ref) < t, (rel(y, y_ref), rel(dv, dv_ref), rel(dl, dl_ref))
+    # deterministic: bit-identical on a second run (gather, no atomics)
+    assert torch.equal(y, K.outlook_fwd(vd, lgd, heads, scale, simt=simt))
+    dv2, dl2 = K.outlook_bwd(vd, lgd, dyd, heads, scale, simt=simt)
+    assert torch.equal(dv, dv2) and torch.equal(dl, dl2)
+
+
+def test_outlook_module_golden():
+    """kernel path == the reference module's output stored by oracle/gen_golden.py"""
+    dev = need_gpu()
+    import autoprog_b200.volo as V
+    fx = torch.load(os.path.join(G, 'outlook_attention.pt'))
+    for name, c in fx.items():
+        m = V.OutlookAttention(32 * c['heads'], c['heads'], kernel_size=3, padding=1, stride=2).to(dev)
+        m.load_state_dict(c['sd'])
+        x = c['x'].to(dev).requires_grad_(True)
+        y = m(x)
+        y.backward(c['dy'].to(dev))
+        assert rel(y, c['y']) < 1e-5, name
+        assert rel(x.grad, c['dx']) < 1e-5, name
+        for k, g in c['grads'].items():
+            assert rel(dict(m.named_parameters())[k].grad, g) < 1e-5, (name, k)
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('cfg', [(4, 9, 10, True), (3, 196, 1000, True), (5, 17, 24, False), (2, 33, 13, True), (6, 1, 8, True)])
+def test_tlce(cfg, dtype):
+    dev = need_gpu()
+    B, N, C, is3d = cfg
+    torch.manual_seed(B * N + C)
+    xc, xa = q(torch.randn(B, C) * 2, dtype), q(torch.randn(B, N, C) * 2, dtype)
+    t = (torch.softmax(torch.randn(B, C, 2 + N), 1) * 1.2).float() if is3d else torch.softmax(torch.randn(B, C), 1).float()
+    for bbox, wd, wc in [((0, 0, 0, 0), 0.5, 1.0), ((0, 1, 2, 3), 1.0, 1.0), ((0, 0, 1, 1), 0.5, 0.0)]:
+        area = (bbox[2] - bbox[0]) * (bbox[3] - bbox[1])
+        if area > N:
+            continue
+        loss_ref, dc_ref, da_ref = O.token_label_ce_grads(xc, xa, bbox, t.double(), wd, wc)
+        loss, dc, da = K.tlce_fwd_bwd(xc.to(dev, dtype), xa.to(dev, dtype), t.to(dev), area, wc, wd)
+        tl = tol(dtype)
+        assert abs(float(loss) - float(loss_ref)) < 2e-6 * abs(float(loss_ref)) + 1e-7
+        assert rel(da, da_ref) < tl, rel(da, da_ref)
+        if wc > 0:
+            assert rel(dc, dc_ref) < tl
+        else:
+            assert float(dc.float().abs().max()) == 0.0
+
+
+def test_tlce_golden_and_variants():
+    dev = need_gpu()
+    import autoprog_b200 as A
+    fx = torch.load(os.path.join(G, 'losses.pt'))
+    xc0, xa0 = fx['x_cls'].float().to(dev), fx['x_aux'].float().to(dev)
+    for key, c in fx['cases'].items():
+        parts = key.split('|')
+        if parts[0] == 'tlce':
+            bbox, t = eval(parts[1]), fx[parts[2]].float().to(dev)
+            xc, xa = xc0.clone().requires_grad_(True), xa0.clone().requires_grad_(True)
+            crit = A.TokenLabelCrossEntropy(dense_weight=float(parts[3]), cls_weight=float(parts[4]), classes=10)
+            loss = crit((xc, xa, bbox), t)
+            (loss * 3.0).backward()      # non-unit upstream gradient
+            assert abs(float(loss) - float(c['loss'])) < 1e-5 * abs(float(c['loss']))
+            assert rel(xa.grad, 3.0 * c['daux']) < 1e-5
+            if float(c['dcls'].abs().max()) > 0:
+                assert rel(xc.grad, 3.0 * c['dcls']) < 1e-5
+        elif parts[0] == 'gt':
+            crit = A.TokenLabelGTCrossEntropy(dense_weight=0.5, cls_weight=1.0, classes=10)
+            loss = crit((xc0, xa0, eval(parts[1])), fx['t3'].float().to(dev))
+            assert abs(float(loss) - float(c['loss'])) < 1e-5 * abs(float(c['loss']))
+    C = xc0.shape[-1]
+    t2, t3 = fx['t2'].float().to(dev), fx['t3'].float().to(dev)
+    assert abs(float(A.SoftTargetCrossEntropy()(xc0, t2)) - float(fx['cases']['soft']['loss'])) < 1e-5
+    assert abs(float(A.SoftTargetCrossEntropy()(xa0.reshape(-1, C)[:8].contiguous(), t2)) - float(fx['cases']['soft_rep']['loss'])) < 1e-5
+    assert abs(float(A.TokenLabelSoftTargetCrossEntropy()(xc0, t3[:, :, :2])) - float(fx['cases']['tlsoft']['loss'])) < 1e-5
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('rows,C', [(37, 192), (64, 384), (5, 64), (3, 1000), (130, 256), (9, 32)])
+def test_layernorm_residual(rows, C, dtype):
+    dev = need_gpu()
+    torch.manual_seed(rows + C)
+    B = 1 if rows % 2 else 2
+    rps = rows // B
+    x = torch.randn(rows, C).float().double() * 2 + 0.5
+    r = q(torch.randn(rows, C), dtype)
+    rs = torch.tensor([1.25, 0.0][:B]).double()
+    g, b = (1 + 0.2 * torch.randn(C)).float().double(), (0.1 * torch.randn(C)).float().double()
+    dy = q(torch.randn(rows, C), dtype)
+    dres = torch.randn(rows, C).float().double()
+    xr = x.clone().requires_grad_(True)
+    rr = r.clone().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    xs_ref = xr + rs.repeat_interleave(rps)[:, None] * rr
+    y_ref = O.layer_norm(xs_ref, gr, br, 1e-5)
+    (y_ref * dy).sum().backward(retain_graph=True)
+    xs_ref.backward(dres)
+    xs, y, mean, rstd = K.ln_fwd(x.float().to(dev), g.float().to(dev), b.float().to(dev), 1e-5, dtype, r=r.to(dev, dtype),
+                                 rs=rs.float().to(dev), rows_per_sample=rps)
+    t = tol(dtype)
+    assert rel(xs, xs_ref) < 1e-6 and rel(y, y_ref) < t
+    dxs, dr, dg, db = K.ln_bwd(dy.to(dev, dtype), xs, mean, rstd, g.float().to(dev), dres=dres.float().to(dev), want_dr=True,
+                               rs=rs.float().to(dev), rows_per_sample=rps)
+    assert rel(dxs, xr.grad) < max(t * 0.1, 1e-5), rel(dxs, xr.grad)
+    assert rel(dr, rr.grad) < t and rel(dg, gr.grad) < max(t * 0.1, 1e-5) and rel(db, br.grad) < max(t * 0.1, 1e-5)
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('M,N,Kd', [(64, 64, 16), (100, 486, 192), (7, 5, 3), (256, 192, 576), (33, 1000, 384)])
+@pytest.mark.parametrize('ta,tb', [(False, False), (False, True), (True, True)])
+def test_gemm_simt(M, N, Kd, ta, tb, dtype):
+    dev = need_gpu()
+    torch.manual_seed(M + N + Kd)
+    a, b = q(torch.randn(M, Kd), dtype), q(torch.randn(N, Kd), dtype)
+    bias = torch.randn(N).float().double()
+    ref = a @ b.t() + bias
+    A_ = (a.t().contiguous() if ta else a).to(dev, dtype)
+    B_ = (b.t().contiguous() if tb else b).to(dev, dtype)
+    lib = K.lib()
+    out = torch.empty(M, N, device=dev, dtype=dtype)
+    K.check(lib.apb_gemm_simt(A_.data_ptr(), B_.data_ptr(), out.data_ptr(), bias.float().to(dev).data_ptr(), None, M, N, Kd,
+                              int(ta), int(tb), 0, K.dt(A_), K.dt(out), torch.cuda.current_stream().cuda_stream), 'gemm')
+    assert rel(out, ref) < (2e-6 if dtype == torch.float32 else 5e-3)
+    # GELU / dGELU epilogues
+    aux = torch.empty_like(out)
+    K.check(lib.apb_gemm_simt(A_.data_ptr(), B_.data_ptr(), out.data_ptr(), bias.float().to(dev).data_ptr(), aux.data_ptr(), M, N,
+                              Kd, int(ta), int(tb), 1, K.dt(A_), K.dt(out), torch.cuda.current_stream().cuda_stream), 'gemm')
+    assert rel(aux, ref) < (2e-6 if dtype == torch.float32 else 5e-3)
+    assert rel(out, O.gelu(aux.double().cpu())) < (2e-6 if dtype == torch.float32 else 5e-3)
+    K.check(lib.apb_gemm_simt(A_.data_ptr(), B_.data_ptr(), out.data_ptr(), None, aux.data_ptr(), M, N, Kd, int(ta), int(tb), 2,
+                              K.dt(A_), K.dt(out), torch.cuda.current_stream().cuda_stream), 'gemm')
+    u = aux.double().cpu().requires_grad_(True)
+    O.gelu(u).backward(a @ b.t())
+    assert rel(out, u.grad) < (3e-6 if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('B,N,heads,D', [(2, 196, 2, 32), (1, 49, 3, 32), (2, 100, 1, 64), (1, 7, 2, 16), (1, 576, 1, 32)])
+def test_mhsa_core(B, N, heads, D, dtype):
+    dev = need_gpu()
+    torch.manual_seed(N + heads)
+    qkv = q(torch.randn(B, N, 3 * heads * D), dtype).requires_grad_(True)
+    do = q(torch.randn(B, N, heads * D), dtype)
+    scale = D ** -0.5
+    ref = O.mhsa_core(qkv, heads, scale)
+    ref.backward(do)
+    out, lse = K.mhsa_fwd(qkv.detach().to(dev, dtype), heads, scale)
+    dqkv = K.mhsa_bwd(qkv.detach().to(dev, dtype), out, do.to(dev, dtype), lse, heads, scale)
+    t = tol(dtype)
+    assert rel(out, ref) < t and rel(dqkv, qkv.grad) < t, (rel(out, ref), rel(dqkv, qkv.grad))
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('B,N,heads,D', [(3, 197, 2, 32), (2, 50, 4, 32), (1, 5, 1, 64)])
+def test_class_attn_core(B, N, heads, D, dtype):
+    dev = need_gpu()
+    torch.manual_seed(N)
+    qq = q(torch.randn(B, heads * D), dtype).requires_grad_(True)
+    kv = q(torch.randn(B, N, 2 * heads * D), dtype).requires_grad_(True)
+    do = q(torch.randn(B, heads * D), dtype)
+    ref = O.class_attn_core(qq, kv, heads, D ** -0.5)
+    ref.backward(do)
+    out = K.class_attn_fwd(qq.detach().to(dev, dtype), kv.detach().to(dev, dtype), heads, D ** -0.5)
+    dq, dkv = K.class_attn_bwd(qq.detach().to(dev, dtype), kv.detach().to(dev, dtype), do.to(dev, dtype), heads, D ** -0.5)
+    t = tol(dtype)
+    assert rel(out, ref) < t and rel(dq, qq.grad) < t and rel(dkv, kv.grad) < t
+
+
+@pytest.mark.parametrize('dtype', DT)
+def test_layout_kernels(dtype):
+    dev = need_gpu()
+    torch.manual_seed(1)
+    for (B, H, W, C) in [(2, 7, 6, 8), (1, 28, 28, 192), (3, 5, 5, 3)]:
+        x = q(torch.randn(B, H, W, C), dtype)
+        xd = x.to(dev, dtype)
+        assert rel(K.avgpool2_fwd(xd), O.avgpool2_ceil(x)) < tol(dtype)
+        xg = x.clone().requires_grad_(True)
+        dyp = q(torch.randn(B, (H + 1) // 2, (W + 1) // 2, C), dtype)
+        O.avgpool2_ceil(xg).backward(dyp)
+        assert rel(K.avgpool2_bwd(dyp.to(dev, dtype), H, W), xg.grad) < tol(dtype)
+        box = (1, 0, min(4, H), min(3, W))
+        assert torch.equal(K.flip_in_box(xd, box).cpu().double(), O.flip_in_box(x, box))
+        assert torch.equal(K.flip_in_box(K.flip_in_box(xd, box), box), xd)
+        for p in (2, 4):
+            if H < p or W < p:
+                continue
+            rows = K.patchify(xd, p)
+            ref = torch.nn.functional.unfold(x.permute(0, 3, 1, 2), p, stride=p)          # [B, C*p*p, L] (c,kh,kw)
+            L = ref.shape[-1]
+            ref = ref.reshape(B, C, p, p, L).permute(0, 4, 2, 3, 1).reshape(B * L, p * p * C)
+            assert torch.equal(rows.cpu().double(), ref)
+            back = K.unpatchify(rows, B, H, W, C, p).cpu().double()
+            mask = torch.zeros(H, W, dtype=torch.bool)
+            mask[:H // p * p, :W // p * p] = True
+            assert torch.equal(back[:, mask], x[:, mask]) and float(back[:, ~mask].abs().sum()) == 0.0
+
+
+def test_bicubic_pos_embed_golden():
+    dev = need_gpu()
+    fx = torch.load(os.path.join(G, 'pos_embed.pt'))
+    pos = fx['pos'][0].float().to(dev).contiguous()
+    h, w, C = pos.shape
+    for g, want in fx['out'].items():
+        if g == (h, w):
+            continue
+        got = K.bicubic_resize(pos, g[0], g[1])
+        assert rel(got, want[0]) < 1e-5, (g, rel(got, want[0]))
+        # backward is the exact transpose: <R p, d> == <p, R^T d>
+        d = torch.randn(g[0], g[1], C, device=dev)
+        lhs = float((got.double() * d.double()).sum())
+        rhs = float((pos.double() * K.bicubic_resize_bwd(d, h, w).double()).sum())
+        assert abs(lhs - rhs) < 1e-4 * max(1.0, abs(lhs))
+
+
+def test_misc_elementwise_and_optimizer():
+    dev = need_gpu()
+    torch.manual_seed(2)
+    x = torch.randn(4, 1000, device=dev)
+    assert rel(K.gelu_fwd(x), O.gelu(x.double().cpu())) < 1e-6
+    assert torch.equal(K.cast(K.cast(x, torch.bfloat16), torch.float32), x.bfloat16().float())
+    rs = torch.tensor([0., 1., 2., .5], device=dev)
+    assert rel(K.scale_cast(x, torch.float32, rs), x * rs[:, None]) < 1e-7
+    r = torch.randn(4, 1000, device=dev).bfloat16()
+    assert rel(K.residual_add(x, r, rs), x + rs[:, None] * r.float()) < 1e-6
+    assert rel(K.colsum(x), x.double().sum(0)) < 1e-6
+    big = torch.randn(5000, 96, device=dev)
+    assert rel(K.colsum(big), big.double().sum(0)) < 1e-5
+    # fused AdamW + EMA vs torch.optim.AdamW + explicit lerp
+    p = torch.randn(10007, device=dev)
+    ref_p = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    emas = [p.clone(), p.clone()]
+    ref_emas = [p.clone(), p.clone()]
+    decays = [0.998, 0.9996]
+    shadow = torch.empty_like(p, dtype=torch.bfloat16)
+    for step in range(1, 4):
+        g = torch.randn_like(p)
+        ref_p.grad = g.clone()
+        opt.step()
+        for e, d in zip(ref_emas, decays):
+            e.mul_(d).add_(ref_p.detach(), alpha=1 - d)
+        K.adamw_ema(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.05, 1 - 0.9 ** step, 1 - 0.999 ** step, emas, decays, shadow)
+    assert rel(p, ref_p) < 1e-6 and rel(emas[0], ref_emas[0]) < 1e-6 and rel(emas[1], ref_emas[1]) < 1e-6
+    assert torch.equal(shadow, p.bfloat16())
+
+
+def test_outlook_full_size_properties():
+    """BASELINE-size checks through size-independent properties: linearity in v, and softmax-shift invariance."""
+    dev = need_gpu()
+    torch.manual_seed(3)
+    B, H, W, heads = 64, 28, 28, 6
+    for dtype in DT:
+        v1 = torch.randn(B, H, W, heads * 32, device=dev).to(dtype)
+        v2 = torch.randn(B, H, W, heads * 32, device=dev).to(dtype)
+        lg = (torch.randn(B, 14, 14, heads * 81, device=dev) * 2).to(dtype)
+        s = 32 ** -0.5
+        y1, y2 = K.outlook_fwd(v1, lg, heads, s), K.outlook_fwd(v2, lg, heads, s)
+        y12 = K.outlook_fwd((v1.float() + v2.float()).to(dtype), lg, heads, s)
+        assert rel(y12, y1.float() + y2.float()) < (1e-5 if dtype == torch.float32 else 2e-2)
+        if dtype == torch.float32:   # adding a constant to all logits of a row leaves the softmax unchanged
+            y3 = K.outlook_fwd(v1, lg + 1.5, heads, s)
+            assert rel(y3, y1) < 1e-5
+            # all-equal logits = uniform 1/9 weights: every output is (1/9) * sum over the window, folded
+            yu = K.outlook_fwd(v1, torch.zeros_like(lg), heads, s)
+            ref = O._fold(O._windows(v1[:2].double().cpu(), 14, 14).mean(3, keepdim=True).expand(-1, -1, -1, 9, -1).contiguous(), H, W)
+            assert rel(yu[:2], ref) < 1e-5
