@@ -29,7 +29,8 @@ SIGNATURES = {
     'apb_colsum_workspace_floats': (_ll, [_ll, _i]),
     'apb_colsum': (_i, [_vp, _ll, _i, _vp, _i, _vp, _i, _vp]),
     'apb_gemm_simt': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    'apb_gemm_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'apb_gemm_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'apb_gemm_tc_suggest_split': (_i, [_i, _i, _i]),
     'apb_mhsa_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_mhsa_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_class_attn_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),

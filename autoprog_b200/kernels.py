@@ -139,9 +139,22 @@ def gemm(a, b, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = Fa
         aux = torch.empty((M, N), device=a.device, dtype=out_dtype)
     assert a.numel() == M * K and b.numel() == N * K, (a.shape, b.shape, M, N, K)
     use_tc = a.dtype == torch.bfloat16 and not _FORCE_SIMT and tc_supported(M, N, K)
-    fn = lib().apb_gemm_tc if use_tc else lib().apb_gemm_simt
-    check(fn(_p(a), _p(b), _p(out), _p(bias), _p(aux), M, N, K, int(trans_a), int(trans_b), epilogue, dt(a),
-             _CODES[out_dtype], _st()), 'gemm_tc' if use_tc else 'gemm_simt')
+    if not use_tc:
+        check(lib().apb_gemm_simt(_p(a), _p(b), _p(out), _p(bias), _p(aux), M, N, K, int(trans_a), int(trans_b), epilogue,
+                                  dt(a), _CODES[out_dtype], _st()), 'gemm_simt')
+        return (out, aux) if epilogue == EPI_GELU else out
+    split = 1
+    if out_dtype == torch.float32 and epilogue == EPI_NONE and bias is None:
+        split = int(lib().apb_gemm_tc_suggest_split(M, N, K))
+    if split > 1:   # deterministic split-K: fp32 partial tiles, then a fixed-order sum over the split dim
+        parts = torch.empty((split, M, N), device=a.device, dtype=torch.float32)
+        check(lib().apb_gemm_tc(_p(a), _p(b), _p(parts), None, None, M, N, K, int(trans_a), int(trans_b), 0, dt(a), F32,
+                                split, _st()), 'gemm_tc(split-k)')
+        ws = torch.empty(M * N, device=a.device, dtype=torch.float32)
+        check(lib().apb_colsum(_p(parts), split, M * N, _p(out), 0, _p(ws), F32, _st()), 'gemm_tc(split-k reduce)')
+        return out
+    check(lib().apb_gemm_tc(_p(a), _p(b), _p(out), _p(bias), _p(aux), M, N, K, int(trans_a), int(trans_b), epilogue, dt(a),
+                            _CODES[out_dtype], 1, _st()), 'gemm_tc')
     return (out, aux) if epilogue == EPI_GELU else out
 
 

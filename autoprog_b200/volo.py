@@ -171,7 +171,7 @@ class _ResidualBlock(nn.Module):
         B = x.shape[0]
         rs_attn = _drop_scale(self.drop_path, B, x.device)
         rs_mlp = _drop_scale(self.drop_path, B, x.device)
-        x1, z = self._apply(x, r, rs, rs_attn)
+        x1, z = self._fused(x, r, rs, rs_attn)
         return x1, z, rs_mlp
 
 
@@ -188,7 +188,7 @@ class Outlooker(_ResidualBlock):
         self.norm2 = _make_norm(norm_layer, dim)
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer)
 
-    def _apply(self, x, r, rs, rs_attn):
+    def _fused(self, x, r, rs, rs_attn):
         a = self.attn
         a._check(x.shape[-1])
         if a.v.bias is not None:
@@ -231,7 +231,7 @@ class Transformer(_ResidualBlock):
         self.norm2 = _make_norm(norm_layer, dim)
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer)
 
-    def _apply(self, x, r, rs, rs_attn):
+    def _fused(self, x, r, rs, rs_attn):
         a = self.attn
         return ops.TransformerFn.apply(x, r, rs, rs_attn, a.num_heads, self.norm1.eps, self.norm1.weight, self.norm1.bias,
                                        a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias, self.norm2.weight,

@@ -80,7 +80,10 @@ int apb_colsum(const void* a, long long rows, int C, float* out, int accumulate,
 int apb_gemm_simt(const void* A, const void* B, void* C, const float* bias, void* aux, int M, int N, int K, int trans_a,
                   int trans_b, int epilogue, int in_dtype, int out_dtype, apb_stream_t stream);
 int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* aux, int M, int N, int K, int trans_a,
-                int trans_b, int epilogue, int in_dtype, int out_dtype, apb_stream_t stream);
+                int trans_b, int epilogue, int in_dtype, int out_dtype, int split_k, apb_stream_t stream);
+/* split_k > 1 (wgrad: few output tiles, very long K): C receives split_k fp32 partial products [split_k][M][N] that
+ * the caller sums in fixed order (apb_colsum over the split dim) -> deterministic; bias/epilogue must be 0/NULL. */
+int apb_gemm_tc_suggest_split(int M, int N, int K);
 
 /* ---- multi-head self-attention core  softmax(q k^T * scale) v  (models/volo.py:188-197)
  * qkv [B,N,3*heads*D] laid out (3, heads, D) per token; out [B,N,heads*D]; lse [B,heads,N] fp32 (saved for bwd).

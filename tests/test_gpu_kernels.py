@@ -303,3 +303,62 @@ def test_outlook_full_size_properties():
             yu = K.outlook_fwd(v1, torch.zeros_like(lg), heads, s)
             ref = O._fold(O._windows(v1[:2].double().cpu(), 14, 14).mean(3, keepdim=True).expand(-1, -1, -1, 9, -1).contiguous(), H, W)
             assert rel(yu[:2], ref) < 1e-5
+
+
+@pytest.mark.parametrize('ta,tb', [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize('M,N,Kd', [(128, 128, 64), (256, 128, 192), (200, 136, 72), (1000, 384, 1152), (392, 1000, 384),
+                                    (8, 8, 8), (130, 72, 200)])
+def test_gemm_tc_vs_fp64(M, N, Kd, ta, tb):
+    """tcgen05 kernel, all four operand-major combinations (fwd NT, dgrad NN, wgrad TN), ragged tiles, epilogues."""
+    dev = need_gpu()
+    torch.manual_seed(M + N + Kd)
+    a, b = q(torch.randn(M, Kd), torch.bfloat16), q(torch.randn(N, Kd), torch.bfloat16)
+    bias = torch.randn(N).float()
+    ref = a @ b.t()
+    A_ = (a.t().contiguous() if ta else a).to(dev, torch.bfloat16)
+    B_ = (b.t().contiguous() if tb else b).to(dev, torch.bfloat16)
+    if not K.tc_supported(M, N, Kd):
+        pytest.skip('outside the TMA envelope')
+    lib = K.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    for out_dtype in (torch.bfloat16, torch.float32):
+        out = torch.zeros(M, N, device=dev, dtype=out_dtype)
+        K.check(lib.apb_gemm_tc(A_.data_ptr(), B_.data_ptr(), out.data_ptr(), bias.to(dev).data_ptr(), None, M, N, Kd, int(ta),
+                                int(tb), 0, K.BF16, K._CODES[out_dtype], 1, st), 'gemm_tc')
+        torch.cuda.synchronize()
+        assert rel(out, ref + bias.double()) < (4e-3 if out_dtype == torch.bfloat16 else 2e-6), (out_dtype, rel(out, ref + bias.double()))
+    # GELU epilogue: aux = pre-activation, out = gelu(aux); dGELU: out = acc * gelu'(aux)
+    out = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+    aux = torch.zeros_like(out)
+    K.check(lib.apb_gemm_tc(A_.data_ptr(), B_.data_ptr(), out.data_ptr(), bias.to(dev).data_ptr(), aux.data_ptr(), M, N, Kd, int(ta),
+                            int(tb), 1, K.BF16, K.BF16, 1, st), 'gemm_tc')
+    assert rel(aux, ref + bias.double()) < 4e-3 and rel(out, O.gelu(aux.double().cpu())) < 4e-3
+    K.check(lib.apb_gemm_tc(A_.data_ptr(), B_.data_ptr(), out.data_ptr(), None, aux.data_ptr(), M, N, Kd, int(ta), int(tb), 2,
+                            K.BF16, K.BF16, 1, st), 'gemm_tc')
+    u = aux.double().cpu().requires_grad_(True)
+    O.gelu(u).backward(ref)
+    assert rel(out, u.grad) < 5e-3
+    # split-K partials + fixed-order reduction (the wgrad path) through the binding
+    if Kd >= 192:
+        for split in (2, 3):
+            kb = (Kd + 63) // 64
+            per = (kb + split - 1) // split
+            if (kb + per - 1) // per != split:
+                continue
+            parts = torch.zeros(split, M, N, device=dev)
+            K.check(lib.apb_gemm_tc(A_.data_ptr(), B_.data_ptr(), parts.data_ptr(), None, None, M, N, Kd, int(ta), int(tb), 0,
+                                    K.BF16, K.F32, split, st), 'gemm_tc')
+            assert rel(parts.sum(0), ref) < 2e-6
+
+
+def test_gemm_binding_wgrad_split_k_deterministic():
+    dev = need_gpu()
+    torch.manual_seed(5)
+    M, N, Kd = 25088, 384, 1152          # fc2 of stage 2 at B=128: dW[384,1152] = dY^T[384,25088] . hdn[25088,1152]
+    dy = torch.randn(M, N, device=dev).bfloat16()
+    x = torch.randn(M, Kd, device=dev).bfloat16()
+    dw1 = K.gemm(dy, x, N, Kd, M, trans_a=True, trans_b=True, out_dtype=torch.float32)
+    dw2 = K.gemm(dy, x, N, Kd, M, trans_a=True, trans_b=True, out_dtype=torch.float32)
+    assert torch.equal(dw1, dw2)
+    ref = dy.double().t() @ x.double()
+    assert rel(dw1, ref) < 1e-5
