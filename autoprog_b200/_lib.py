@@ -33,6 +33,8 @@ SIGNATURES = {
     'apb_gemm_tc_suggest_split': (_i, [_i, _i, _i]),
     'apb_mhsa_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_mhsa_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    'apb_mhsa_fwd_simt': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    'apb_mhsa_bwd_simt': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_class_attn_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_class_attn_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_avgpool2_fwd': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

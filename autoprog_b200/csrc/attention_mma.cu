@@ -1,0 +1,381 @@
+// Multi-head self-attention core on tensor cores (bf16 in, fp32 accumulate), head_dim 32 (every VOLO variant).
+//
+// Replaces models/volo.py:193-197 (q@k^T*scale -> softmax -> @v with the [B,heads,N,N] scores materialised) by
+// flash-style kernels: scores live in registers, K/V (or Q/dO) of one (b, head) live in shared memory.
+// N is 64..784 on this path and d=32, so one (b, head) problem is two 196x32x196 products: far below a tcgen05
+// tile (128 x N x 16 per instruction, TMEM round trip per softmax) -- the warp-level mma.sync.m16n8k16 pipe keeps
+// the whole softmax in the accumulator registers and is the right tool at this size.
+//
+//   fwd : CTA = one (b, head); each warp owns 16 query rows, loops over 64-key tiles with an online softmax.
+//   bwd : (1) D[i] = <dO_i, O_i>            (2) dQ : CTA per (b, head), warp per 16 queries, K/V in smem
+//         (3) dK,dV : CTA per (b, head), warp per 16 keys, Q/dO in smem.  No atomics -> deterministic.
+// Layouts: qkv [B,N,3,heads,32], out/dout [B,N,heads,32], lse/D [B,heads,N] fp32.
+#include "common.cuh"
+
+namespace {
+
+constexpr int D = 32;
+constexpr int ROWP = 40;   // padded smem row pitch in bf16 (80 B): conflict-free ldmatrix
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// rows [0,N) of a [N, 32] bf16 matrix with global row stride `gstride` (elements) -> smem [rows_pad][ROWP], tail zeroed
+__device__ __forceinline__ void stage_rows(bf16* s, const bf16* g, size_t gstride, int N, int rows_pad) {
+  for (int e = threadIdx.x; e < rows_pad * 4; e += blockDim.x) {
+    const int n = e >> 2, ch = e & 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (n < N) v = *reinterpret_cast<const uint4*>(g + (size_t)n * gstride + ch * 8);
+    *reinterpret_cast<uint4*>(s + n * ROWP + ch * 8) = v;
+  }
+}
+
+// A-operand fragments (16 rows x 32 channels = 2 k-steps) straight from global; rows >= N read as zero
+__device__ __forceinline__ void load_a_rows(uint32_t (&a)[2][4], const bf16* g, size_t gstride, int row0, int N, int lane) {
+  const int gi = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int r = row0 + gi + (h & 1) * 8;
+      const int c = ks * 16 + 2 * q + (h >> 1) * 8;
+      a[ks][h] = (r < N) ? *reinterpret_cast<const uint32_t*>(g + (size_t)r * gstride + c) : 0u;
+    }
+}
+
+// S[16 x 8] (+)= A[16 x 32] . M[key0..key0+7][0..31]^T  with M rows in smem (B operand "col": contiguous channel pairs)
+__device__ __forceinline__ void mma_rowsT(float (&c)[4], const uint32_t (&a)[2][4], const bf16* sM, int key0, int lane) {
+  uint32_t b[4];
+  ldsm_x4(b, smem_u32(sM + (key0 + (lane & 7)) * ROWP + (lane >> 3) * 8));
+  mma16816(c, a[0], b[0], b[1]);
+  mma16816(c, a[1], b[2], b[3]);
+}
+
+// O[16 x 32] += P[16 x 16 (keys key0..+15)] . M[key0..key0+15][0..31]  (B operand via ldmatrix.trans)
+__device__ __forceinline__ void mma_rows(float (&o)[4][4], const uint32_t (&pa)[4], const bf16* sM, int key0, int lane) {
+  uint32_t b[4];
+  const int mi = lane >> 3, r = lane & 7;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    ldsm_x4_t(b, smem_u32(sM + (key0 + (mi & 1) * 8 + r) * ROWP + half * 16 + (mi >> 1) * 8));
+    mma16816(o[half * 2 + 0], pa, b[0], b[1]);
+    mma16816(o[half * 2 + 1], pa, b[2], b[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256) mhsa_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                                                           float* __restrict__ lse, int N, int heads, float scale,
+                                                           int rows_pad) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16* sK = reinterpret_cast<bf16*>(smraw);
+  bf16* sV = sK + (size_t)rows_pad * ROWP;
+  const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
+  const size_t tok = (size_t)3 * heads * D;
+  const bf16* qb = qkv + (size_t)b * N * tok + (size_t)hd * D;
+  stage_rows(sK, qb + heads * D, tok, N, rows_pad);
+  stage_rows(sV, qb + 2 * heads * D, tok, N, rows_pad);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int gi = lane >> 2, q = lane & 3;
+  const float sl2 = scale * 1.4426950408889634f;
+  for (int row0 = warp * 16; row0 < N; row0 += nwarp * 16) {
+    uint32_t qa[2][4];
+    load_a_rows(qa, qb, tok, row0, N, lane);
+    float o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    for (int k0 = 0; k0 < N; k0 += 64) {
+      float s[8][4];
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb) {
+        s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+        if (k0 + nb * 8 < N) mma_rowsT(s[nb], qa, sK, k0 + nb * 8, lane);
+      }
+      float mt[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int key = k0 + nb * 8 + 2 * q + (j & 1);
+          if (key >= N) s[nb][j] = -INFINITY;
+          mt[j >> 1] = fmaxf(mt[j >> 1], s[nb][j]);
+        }
+      float corr[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float mn = fmaxf(m_run[h], quad_max(mt[h]));
+        corr[h] = exp2f((m_run[h] - mn) * sl2);
+        m_run[h] = mn;
+        l_run[h] *= corr[h];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1]; }
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float pv = exp2f((s[nb][j] - m_run[j >> 1]) * sl2);
+          s[nb][j] = pv;
+          l_run[j >> 1] += pv;
+        }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (k0 + kk * 16 < N) {
+          uint32_t pa[4] = {pack_bf16(s[2 * kk][0], s[2 * kk][1]), pack_bf16(s[2 * kk][2], s[2 * kk][3]),
+                            pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3])};
+          mma_rows(o, pa, sV, k0 + kk * 16, lane);
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float l = quad_sum(l_run[h]);
+      const int r = row0 + gi + h * 8;
+      if (r < N) {
+        const float inv = 1.f / l;
+        bf16* orow = out + ((size_t)b * N + r) * heads * D + (size_t)hd * D;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint32_t*>(orow + i * 8 + 2 * q) = pack_bf16(o[i][2 * h] * inv, o[i][2 * h + 1] * inv);
+        if (q == 0) lse[((size_t)b * heads + hd) * N + r] = m_run[h] * scale + logf(l);
+      }
+    }
+  }
+}
+
+// D[i] = sum_c dO[i][c] * O[i][c]
+__global__ void __launch_bounds__(256) mhsa_rowdot_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout,
+                                                          float* __restrict__ drow, int B, int N, int heads) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, n, head)
+  const long long total = (long long)B * N * heads;
+  if (idx >= total) return;
+  const int hd = (int)(idx % heads);
+  const long long bn = idx / heads;
+  const int n = (int)(bn % N);
+  const int b = (int)(bn / N);
+  const uint4* po = reinterpret_cast<const uint4*>(out + (size_t)idx * D);
+  const uint4* pg = reinterpret_cast<const uint4*>(dout + (size_t)idx * D);
+  float acc = 0.f;
+#pragma unroll
+  for (int v4 = 0; v4 < 4; ++v4) {
+    const uint4 a = po[v4], g = pg[v4];
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&g);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 fa = __bfloat1622float2(ha[t]), fg = __bfloat1622float2(hg[t]);
+      acc = fmaf(fa.x, fg.x, acc);
+      acc = fmaf(fa.y, fg.y, acc);
+    }
+  }
+  drow[((size_t)b * heads + hd) * N + n] = acc;
+}
+
+// dQ: warp per 16 queries; S = Q K^T, P = exp(S*scale - lse), dP = dO V^T, dS = P*(dP - D), dQ = scale * dS K
+__global__ void __launch_bounds__(256) mhsa_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                              const float* __restrict__ lse, const float* __restrict__ drow,
+                                                              bf16* __restrict__ dqkv, int N, int heads, float scale,
+                                                              int rows_pad) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16* sK = reinterpret_cast<bf16*>(smraw);
+  bf16* sV = sK + (size_t)rows_pad * ROWP;
+  const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
+  const size_t tok = (size_t)3 * heads * D, otok = (size_t)heads * D;
+  const bf16* qb = qkv + (size_t)b * N * tok + (size_t)hd * D;
+  const bf16* gb = dout + (size_t)b * N * otok + (size_t)hd * D;
+  stage_rows(sK, qb + heads * D, tok, N, rows_pad);
+  stage_rows(sV, qb + 2 * heads * D, tok, N, rows_pad);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int gi = lane >> 2, q = lane & 3;
+  const float sl2 = scale * 1.4426950408889634f;
+  const float* L = lse + ((size_t)b * heads + hd) * N;
+  const float* Dr = drow + ((size_t)b * heads + hd) * N;
+  for (int row0 = warp * 16; row0 < N; row0 += nwarp * 16) {
+    uint32_t qa[2][4], ga[2][4];
+    load_a_rows(qa, qb, tok, row0, N, lane);
+    load_a_rows(ga, gb, otok, row0, N, lane);
+    float l2[2], dr[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = row0 + gi + h * 8;
+      l2[h] = (r < N) ? L[r] * 1.4426950408889634f : 0.f;
+      dr[h] = (r < N) ? Dr[r] : 0.f;
+    }
+    float dq[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+    for (int k0 = 0; k0 < N; k0 += 16) {
+      float s[2][4], dp[2][4];
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+        dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
+        mma_rowsT(s[nb], qa, sK, k0 + nb * 8, lane);
+        mma_rowsT(dp[nb], ga, sV, k0 + nb * 8, lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int key = k0 + nb * 8 + 2 * q + (j & 1);
+          const float pv = (key < N) ? exp2f(s[nb][j] * sl2 - l2[j >> 1]) : 0.f;
+          s[nb][j] = pv * (dp[nb][j] - dr[j >> 1]);
+        }
+      }
+      uint32_t pa[4] = {pack_bf16(s[0][0], s[0][1]), pack_bf16(s[0][2], s[0][3]), pack_bf16(s[1][0], s[1][1]),
+                        pack_bf16(s[1][2], s[1][3])};
+      mma_rows(dq, pa, sK, k0, lane);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = row0 + gi + h * 8;
+      if (r < N) {
+        bf16* drowp = dqkv + ((size_t)b * N + r) * tok + (size_t)hd * D;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint32_t*>(drowp + i * 8 + 2 * q) = pack_bf16(dq[i][2 * h] * scale, dq[i][2 * h + 1] * scale);
+      }
+    }
+  }
+}
+
+// dK, dV: warp per 16 keys; S^T = K Q^T, P^T = exp(S^T*scale - lse[query]), dV = P^T dO, dP^T = V dO^T,
+// dS^T = P^T*(dP^T - D[query]), dK = scale * dS^T Q.   Q, dO, lse, D of the (b, head) in smem.
+__global__ void __launch_bounds__(256) mhsa_bwd_dkv_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+                                                               const float* __restrict__ lse,
+                                                               const float* __restrict__ drow, bf16* __restrict__ dqkv,
+                                                               int N, int heads, float scale, int rows_pad) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smraw);
+  bf16* sG = sQ + (size_t)rows_pad * ROWP;
+  float* sL = reinterpret_cast<float*>(sG + (size_t)rows_pad * ROWP);
+  float* sD = sL + rows_pad;
+  const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
+  const size_t tok = (size_t)3 * heads * D, otok = (size_t)heads * D;
+  const bf16* qb = qkv + (size_t)b * N * tok + (size_t)hd * D;
+  const bf16* gb = dout + (size_t)b * N * otok + (size_t)hd * D;
+  stage_rows(sQ, qb, tok, N, rows_pad);
+  stage_rows(sG, gb, otok, N, rows_pad);
+  for (int n = threadIdx.x; n < rows_pad; n += blockDim.x) {
+    sL[n] = (n < N) ? lse[((size_t)b * heads + hd) * N + n] * 1.4426950408889634f : 0.f;
+    sD[n] = (n < N) ? drow[((size_t)b * heads + hd) * N + n] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int gi = lane >> 2, q = lane & 3;
+  const float sl2 = scale * 1.4426950408889634f;
+  for (int key0 = warp * 16; key0 < N; key0 += nwarp * 16) {
+    uint32_t ka[2][4], va[2][4];
+    load_a_rows(ka, qb + heads * D, tok, key0, N, lane);
+    load_a_rows(va, qb + 2 * heads * D, tok, key0, N, lane);
+    float dk[4][4], dv[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { dk[i][j] = 0.f; dv[i][j] = 0.f; }
+    for (int i0 = 0; i0 < N; i0 += 16) {
+      float s[2][4], dp[2][4];
+      uint32_t pp[4], ds[4];
+#pragma unroll
+      for (int nb = 0; nb < 2; ++nb) {
+        s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+        dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
+        mma_rowsT(s[nb], ka, sQ, i0 + nb * 8, lane);     // S^T[key][query]
+        mma_rowsT(dp[nb], va, sG, i0 + nb * 8, lane);    // dP^T[key][query]
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int qi = i0 + nb * 8 + 2 * q + (j & 1);
+          const float pv = (qi < N) ? exp2f(s[nb][j] * sl2 - sL[qi]) : 0.f;
+          s[nb][j] = pv;
+          dp[nb][j] = pv * (dp[nb][j] - sD[qi]);
+        }
+        pp[nb * 2 + 0] = pack_bf16(s[nb][0], s[nb][1]);
+        pp[nb * 2 + 1] = pack_bf16(s[nb][2], s[nb][3]);
+        ds[nb * 2 + 0] = pack_bf16(dp[nb][0], dp[nb][1]);
+        ds[nb * 2 + 1] = pack_bf16(dp[nb][2], dp[nb][3]);
+      }
+      mma_rows(dv, pp, sG, i0, lane);
+      mma_rows(dk, ds, sQ, i0, lane);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = key0 + gi + h * 8;
+      if (r < N) {
+        bf16* kp = dqkv + ((size_t)b * N + r) * tok + (size_t)heads * D + (size_t)hd * D;
+        bf16* vp = kp + (size_t)heads * D;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          *reinterpret_cast<uint32_t*>(kp + i * 8 + 2 * q) = pack_bf16(dk[i][2 * h] * scale, dk[i][2 * h + 1] * scale);
+          *reinterpret_cast<uint32_t*>(vp + i * 8 + 2 * q) = pack_bf16(dv[i][2 * h], dv[i][2 * h + 1]);
+        }
+      }
+    }
+  }
+}
+
+int pick_warps(int N) {
+  const int tiles = (N + 15) / 16;
+  const int rounds = (tiles + 7) / 8;
+  return (tiles + rounds - 1) / rounds;
+}
+
+}  // namespace
+
+int apb_mhsa_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, int heads, float scale, cudaStream_t st) {
+  const int rows_pad = (N + 63) / 64 * 64;
+  const size_t smem = (size_t)2 * rows_pad * ROWP * sizeof(bf16);
+  APB_CHECK_ARG(smem <= 227 * 1024, APB_ERR_UNSUPPORTED, "mhsa_fwd_mma: N=%d needs %zu B smem", N, smem);
+  cudaFuncSetAttribute(mhsa_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mhsa_fwd_mma_kernel<<<B * heads, pick_warps(N) * 32, smem, st>>>((const bf16*)qkv, (bf16*)out, lse, N, heads, scale, rows_pad);
+  APB_LAUNCH_CHECK("mhsa_fwd_mma");
+  return 0;
+}
+
+int apb_mhsa_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
+                     int B, int N, int heads, float scale, cudaStream_t st) {
+  const int rows_pad = (N + 15) / 16 * 16;
+  const size_t smem1 = (size_t)2 * rows_pad * ROWP * sizeof(bf16);
+  const size_t smem2 = smem1 + (size_t)2 * rows_pad * sizeof(float);
+  APB_CHECK_ARG(smem2 <= 227 * 1024, APB_ERR_UNSUPPORTED, "mhsa_bwd_mma: N=%d needs %zu B smem", N, smem2);
+  const long long total = (long long)B * N * heads;
+  mhsa_rowdot_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, workspace, B, N, heads);
+  APB_LAUNCH_CHECK("mhsa_rowdot");
+  cudaFuncSetAttribute(mhsa_bwd_dq_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+  cudaFuncSetAttribute(mhsa_bwd_dkv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+  const int threads = pick_warps(N) * 32;
+  mhsa_bwd_dq_mma_kernel<<<B * heads, threads, smem1, st>>>((const bf16*)qkv, (const bf16*)dout, lse, workspace, (bf16*)dqkv, N,
+                                                           heads, scale, rows_pad);
+  APB_LAUNCH_CHECK("mhsa_bwd_dq_mma");
+  mhsa_bwd_dkv_mma_kernel<<<B * heads, threads, smem2, st>>>((const bf16*)qkv, (const bf16*)dout, lse, workspace, (bf16*)dqkv,
+                                                            N, heads, scale, rows_pad);
+  APB_LAUNCH_CHECK("mhsa_bwd_dkv_mma");
+  return 0;
+}

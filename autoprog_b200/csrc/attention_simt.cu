@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(128) class_attn_kernel(const T* __restrict__ q
 
 static int mhsa_q_per_cta(int N) { return N <= 64 ? N : 64; }
 
-int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, int dtype,
+int apb_mhsa_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, int dtype,
                  apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
   APB_CHECK_ARG(B > 0 && N > 0 && heads > 0 && D > 0, APB_ERR_SHAPE, "mhsa_fwd: bad shape");
@@ -299,7 +299,7 @@ int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads
   return 0;
 }
 
-int apb_mhsa_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
+int apb_mhsa_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
                  int B, int N, int heads, int D, float scale, int dtype, apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
   APB_CHECK_ARG(B > 0 && N > 0 && heads > 0 && D > 0, APB_ERR_SHAPE, "mhsa_bwd: bad shape");

@@ -90,6 +90,12 @@ int apb_gemm_tc_suggest_split(int M, int N, int K);
  * bwd: dqkv same layout as qkv; workspace: B*heads*N floats (row dots D_i). */
 int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, int dtype,
                  apb_stream_t stream);
+/* `_simt`: CUDA-core fp32-exact kernels (parity mode, any D <= 64).  The un-suffixed entries pick the tensor-core
+ * (mma.sync bf16, flash-style, scores in registers) kernels for APB_BF16 with D == 32 and the SIMT ones otherwise. */
+int apb_mhsa_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, int dtype,
+                      apb_stream_t stream);
+int apb_mhsa_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                      float* workspace, int B, int N, int heads, int D, float scale, int dtype, apb_stream_t stream);
 int apb_mhsa_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
                  int B, int N, int heads, int D, float scale, int dtype, apb_stream_t stream);
 
