@@ -51,7 +51,8 @@ SIGNATURES = {
     'apb_add': (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
     'apb_gelu_fwd': (_i, [_vp, _vp, _ll, _i, _vp]),
     'apb_gelu_bwd': (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
-    'apb_adamw_ema': (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _f, _f, C.POINTER(_vp), C.POINTER(_f), _i, _vp, _vp]),
+    'apb_adamw_ema': (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, C.POINTER(_vp), C.POINTER(_f), _i, _vp, _vp]),
+    'apb_launch_count': (_ll, []),
 }
 
 _lib = None

@@ -13,3 +13,6 @@ void apb_set_error(const char* fmt, ...) {
 
 extern "C" const char* apb_last_error(void) { return g_err; }
 extern "C" int apb_abi_version(void) { return 1; }
+
+long long g_apb_launches = 0;
+extern "C" long long apb_launch_count(void) { return g_apb_launches; }

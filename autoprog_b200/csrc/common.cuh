@@ -23,8 +23,10 @@ void apb_set_error(const char* fmt, ...);
     }                                             \
   } while (0)
 
+extern long long g_apb_launches;   // kernel launches issued through the library (not thread-exact; evidence counter)
 #define APB_LAUNCH_CHECK(name)                                              \
   do {                                                                      \
+    ++g_apb_launches;                                                       \
     cudaError_t e__ = cudaGetLastError();                                   \
     if (e__ != cudaSuccess) {                                               \
       apb_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \

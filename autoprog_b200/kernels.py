@@ -307,11 +307,16 @@ def gelu_bwd(x, dy):
     return dx
 
 
-def adamw_ema(p, g, m, v, lr, beta1, beta2, eps, wd, bc1, bc2, emas=(), decays=(), shadow=None):
+def adamw_ema(p, g, m, v, hyper, beta1, beta2, eps, wd, emas=(), decays=(), shadow=None):
+    """hyper: device fp32 tensor [lr, 1-beta1^t, sqrt(1-beta2^t)]."""
     n = p.numel()
     k = len(emas)
     ptrs = (C.c_void_p * max(k, 1))(*[e.data_ptr() for e in emas])
     dec = (C.c_float * max(k, 1))(*[float(d) for d in decays])
-    check(lib().apb_adamw_ema(_p(p), _p(g), _p(m), _p(v), n, lr, beta1, beta2, eps, wd, bc1, bc2,
+    check(lib().apb_adamw_ema(_p(p), _p(g), _p(m), _p(v), n, _p(hyper), beta1, beta2, eps, wd,
                               C.cast(ptrs, C.POINTER(C.c_void_p)), C.cast(dec, C.POINTER(C.c_float)), k, _p(shadow), _st()),
           'adamw_ema')
+
+
+def launch_count() -> int:
+    return int(lib().apb_launch_count())

@@ -48,12 +48,12 @@ def wcast(p: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
         return src
     key = id(p)
     ent = _WCACHE.get(key)
-    if ent is not None and ent[0] == p._version and ent[1] == p.data_ptr() and ent[2].shape == p.shape:
+    if ent is not None and ent[1] == p.data_ptr() and ent[2].shape == p.shape and (ent[3] or ent[0] == p._version):
         return ent[2]
     t = K.cast(src, dtype)
     if ent is None:
         weakref.finalize(p, _WCACHE.pop, key, None)
-    _WCACHE[key] = (p._version, p.data_ptr(), t)
+    _WCACHE[key] = (p._version, p.data_ptr(), t, False)
     return t
 
 
@@ -61,7 +61,15 @@ def register_shadow(p: torch.Tensor, shadow: torch.Tensor) -> None:
     """Let a fused optimizer publish the bf16 copy it wrote (skips the cast kernel on the next forward)."""
     if id(p) not in _WCACHE:
         weakref.finalize(p, _WCACHE.pop, id(p), None)
-    _WCACHE[id(p)] = (p._version, p.data_ptr(), shadow)
+    _WCACHE[id(p)] = (p._version, p.data_ptr(), shadow, True)   # True: kept fresh by its owner, never stale
+
+
+def invalidate_derived_caches() -> None:
+    """Called by optimizers that update parameters through raw pointers (no autograd version bump): drops every cached
+    re-laid-out / cast copy except the shadows the optimizer itself keeps fresh."""
+    _CONVW.clear()
+    for k in [k for k, v in _WCACHE.items() if not v[3]]:
+        del _WCACHE[k]
 
 
 def _c(t: torch.Tensor) -> torch.Tensor:

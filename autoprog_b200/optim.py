@@ -1,0 +1,83 @@
+"""Fused AdamW + multi-EMA optimizer over flat parameter storage.
+
+Semantics = `torch.optim.AdamW` (what timm's `create_optimizer(opt='adamw')` builds, main_prog.py:484) with timm's
+no-weight-decay filter, followed by `ModelEmaV2.update` for every attached EMA model (main_prog.py:1032-1033) --
+executed as ONE kernel launch per parameter group that also refreshes the bf16 compute copies.
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+from . import ops
+from .flat import FlatState
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    def __init__(self, model: nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.05,
+                 ema_models: Sequence[nn.Module] = (), ema_decays: Sequence[float] = (), flat: Optional[FlatState] = None):
+        assert len(ema_models) == len(ema_decays)
+        self.flat = flat or FlatState(model, weight_decay)
+        groups = [dict(params=g.params, weight_decay=wd) for g, wd in zip(self.flat.groups, self.flat.weight_decays)]
+        super().__init__(groups, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.exp_avg = [torch.zeros_like(g.flat_p) for g in self.flat.groups]
+        self.exp_avg_sq = [torch.zeros_like(g.flat_p) for g in self.flat.groups]
+        self.step_count = 0
+        dev = self.flat.groups[0].flat_p.device
+        self._hyper_host = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in self.flat.groups]
+        self._hyper_dev = [torch.zeros(3, device=dev, dtype=torch.float32) for _ in self.flat.groups]
+        self.ema_models = list(ema_models)
+        self.ema_decays = [float(d) for d in ema_decays]
+        self.ema_flats = [self.flat.flat_like(e) for e in self.ema_models]     # [ema][group] -> flat fp32
+        for g in self.flat.groups:                                            # publish the bf16 copies the kernel keeps fresh
+            if g.shadow is not None:
+                for p, s in zip(g.params, g.views(g.shadow)):
+                    if p.dim() == 2:
+                        ops.register_shadow(p, s)
+
+    def zero_grad(self, set_to_none: bool = False):
+        self.flat.zero_grad()
+
+    def prepare_step(self):
+        """Host part of a step: bump the step counter and stage {lr, bias corrections} in pinned memory."""
+        self.step_count += 1
+        for gi, group in enumerate(self.param_groups):
+            b1, b2 = group['betas']
+            h = self._hyper_host[gi]
+            h[0] = group['lr']
+            h[1] = 1.0 - b1 ** self.step_count
+            h[2] = math.sqrt(1.0 - b2 ** self.step_count)
+
+    @torch.no_grad()
+    def launch_step(self):
+        """Device part of a step (CUDA-graph capturable: reads the pinned hyper-parameters at replay time)."""
+        self.flat.ensure_grad_views()
+        for gi, (g, group) in enumerate(zip(self.flat.groups, self.param_groups)):
+            self._hyper_dev[gi].copy_(self._hyper_host[gi], non_blocking=True)
+            b1, b2 = group['betas']
+            K.adamw_ema(g.flat_p, g.flat_g, self.exp_avg[gi], self.exp_avg_sq[gi], self._hyper_dev[gi], b1, b2, group['eps'],
+                        group['weight_decay'], [ef[gi] for ef in self.ema_flats], self.ema_decays, g.shadow)
+        ops.invalidate_derived_caches()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        self.prepare_step()
+        self.launch_step()
+        self.update_ema_buffers()
+        return loss
+
+    @torch.no_grad()
+    def update_ema_buffers(self):
+        """ModelEmaV2 also averages buffers (BatchNorm running stats); they are tiny, so plain torch ops."""
+        src = dict(self.flat.model.named_buffers())
+        for ema, d in zip(self.ema_models, self.ema_decays):
+            for n, b in ema.named_buffers():
+                if b.dtype.is_floating_point:
+                    b.mul_(d).add_(src[n].detach(), alpha=1.0 - d)
+                else:
+                    b.copy_(src[n])

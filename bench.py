@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Benchmark of the AutoProg hot path: volo_d1 training step (fwd + TokenLabelCrossEntropy + bwd + AdamW/EMA step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` = whole-job train images/sec with inputs resident in HBM; `e2e` = the same
+through the public API with pinned HOST buffers (H2D of images + token labels and D2H of the loss every step);
+`roofline` = the dominant kernel (tcgen05 GEMM) measured in situ with CUDA events; `cpu_baseline` = the oracle port
+of the reference's PyTorch path on this box's host cores.  `--impl reference` times that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = 'volo_d1 (== volo_h12_l18) AutoProg final stage: 224px, depth 18, per-GPU batch 128, bf16, TokenLabelCE(dense 0.5)'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=128, help='per-GPU batch (scripts/train_autoprog.sh: -b 128)')
+    ap.add_argument('--model', default='volo_d1')
+    ap.add_argument('--res', type=int, default=224)
+    ap.add_argument('--no-ema', action='store_true')
+    ap.add_argument('--cpu-steps', type=int, default=3)
+    ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--fp32', action='store_true', help='fp32 parity mode (CUDA-core kernels)')
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's PyTorch path (BASELINE.json configs[0]: batch 4, fp32, 224px)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_path_images_per_sec(steps: int, warmup: int, model_name: str, res: int, batch: int = 4):
+    import numpy as np
+    import torch
+    from oracle import volo_cpu as O
+    import autoprog_b200 as A
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    arch = O.VoloArch.named(model_name, img_size=224)
+    m = A.create_model(model_name, img_size=224)            # only used as a container of correctly shaped weights
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in m.state_dict().items()}
+    x = torch.randn(batch, 3, res, res)
+    g = res // 16
+    tgt = torch.softmax(torch.randn(batch, 1000, 2 + g * g), dim=1)
+    times = []
+    for it in range(warmup + steps):
+        for v in sd.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        lam = np.random.beta(1.0, 1.0)
+        bbox = O.rand_bbox(g, g, lam)
+        out = O.volo_forward(sd, x, arch, train=True, bbox=bbox)
+        loss = O.token_label_ce(out[0], out[1], out[2], tgt, dense_weight=0.5)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    return batch / med, cores, f'{steps} steps of batch {batch} @ {res}px fp32 fwd+loss+bwd (median), {cores} torch threads'
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 6))
+    v, cores, sample = cpu_path_images_per_sec(steps, min(args.warmup, 2), args.model, args.res)
+    line = {
+        'impl': 'reference', 'metric': 'train images/sec', 'value': round(v, 3), 'unit': 'images/s', 'n_gpus': args.gpus,
+        'steps': steps, 'warmup': min(args.warmup, 2), 'ms_per_step': round(4 / v * 1e3, 2), 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'note': 'reference PyTorch path restated in oracle/volo_cpu.py, CPU, bounded sample batch 4'},
+        'cpu_baseline': {'value': round(v, 3), 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': round(v, 3), 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+    if args.gpus > 1 and 'RANK' not in os.environ:     # convenience: re-launch under torchrun
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', '29531', os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import autoprog_b200 as A
+    from autoprog_b200 import kernels as K
+    from autoprog_b200.optim import FusedAdamW
+    from autoprog_b200.ddp import DistributedDataParallel
+
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.manual_seed(0)
+    np.random.seed(0 + rank)
+    B, res = args.batch, args.res
+    g = res // 16
+
+    model = A.create_model(args.model, img_size=224, drop_path_rate=0.1).to(dev)
+    import copy
+    decays = [] if args.no_ema else [0.998, 0.9986, 0.999, 0.9996]            # scripts/train_autoprog.sh
+    emas = [copy.deepcopy(model).eval() for _ in decays]
+    for e in emas:
+        for p in e.parameters():
+            p.requires_grad_(False)
+    opt = FusedAdamW(model, lr=1.6e-3 * (B * world) / 1024.0, weight_decay=0.05, ema_models=emas, ema_decays=decays)
+    net = DistributedDataParallel(model, flat=opt.flat) if world > 1 else model
+    crit = A.TokenLabelCrossEntropy(dense_weight=0.5, cls_weight=1.0)
+    bf16 = not args.fp32
+
+    def train_step(x, tgt):
+        opt.zero_grad()
+        with A.autocast(enabled=bf16):
+            out = net(x)
+            loss = crit(out, tgt)
+        loss.backward()
+        opt.step()
+        return loss
+
+    x_dev = torch.randn(B, 3, res, res, device=dev)
+    t_dev = torch.softmax(torch.randn(B, 1000, 2 + g * g, device=dev), dim=1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident arm ----------------------------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        train_step(x_dev, t_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = K.launch_count()
+    ms = timed(lambda: train_step(x_dev, t_dev), args.steps)
+    launches = K.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * world * args.steps / (ms / 1e3)
+
+    # ---- end-to-end arm: pinned host buffers, H2D every step on a copy stream, loss read back every step ------------
+    e2e = None
+    if not args.skip_e2e:
+        hx = [torch.randn(B, 3, res, res).pin_memory() for _ in range(2)]
+        ht = [torch.softmax(torch.randn(B, 1000, 2 + g * g), dim=1).pin_memory() for _ in range(2)]
+        dx = [torch.empty_like(x_dev) for _ in range(2)]
+        dtg = [torch.empty_like(t_dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        state = {'i': 0, 'loss': 0.0}
+
+        def prefetch(slot):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                dx[slot].copy_(hx[slot], non_blocking=True)
+                dtg[slot].copy_(ht[slot], non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def e2e_step():
+            slot = state['i'] & 1
+            torch.cuda.current_stream().wait_event(ready[slot])
+            prefetch(slot ^ 1)                      # next batch streams in while this step computes (tlt PrefetchLoader)
+            loss = train_step(dx[slot], dtg[slot])
+            consumed[slot].record()
+            state['loss'] = float(loss.item())      # D2H of the step's result
+            state['i'] += 1
+
+        for s in range(2):
+            consumed[s].record()
+        prefetch(0)
+        for _ in range(3):
+            e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+        e2e = {'value': round(B * world * args.steps / (ms_e2e / 1e3), 1), 'unit': 'images/s',
+               'h2d_bytes_per_step': int(hx[0].numel() * 4 + ht[0].numel() * 4) * world, 'd2h_bytes_per_step': 4 * world,
+               'ms_per_step': round(ms_e2e / args.steps, 3), 'last_loss': state['loss']}
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM), in situ: one extra step with every GEMM launch bracketed by events
+    roof = None
+    extra = {}
+    if rank == 0:
+        roof, extra = measure_rooflines(train_step, x_dev, t_dev, K, torch, B, bf16)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        v, cores, sample = cpu_path_images_per_sec(args.cpu_steps, 1, args.model, args.res)
+        cpu = {'value': round(v, 3), 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample}
+
+    if rank == 0:
+        line = {
+            'metric': 'train images/sec', 'value': round(value, 1), 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(3, args.warmup), 'ms_per_step': round(ms / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'bf16' if bf16 else 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'model': args.model, 'res': res, 'per_gpu_batch': B, 'global_batch': B * world,
+                       'parallelism': f'dp{world}', 'optimizer': f'fused AdamW + {len(decays)} EMA', 'drop_path': 0.1,
+                       'l2': 'per-step working set (activations ~7 GB) exceeds the 126 MB L2; no explicit flush'},
+            'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_rooflines(train_step, x, t, K, torch, B, bf16):
+    """Wrap the GEMM and OutlookAttention entry points with CUDA events for ONE extra (untimed) step."""
+    peaks = {'hbm_gbs': 6650.0, 'bf16_tflops_sustained': 1400.0, 'src': 'fallback'}
+    try:
+        pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        peaks = {'hbm_gbs': pk['hbm_gbs'], 'bf16_tflops_sustained': pk['bf16_tflops_sustained'], 'src': 'measured'}
+    except Exception:
+        pass
+    rec = {'gemm': [], 'outlook_fwd': [], 'outlook_bwd': [], 'tlce': []}
+    orig = {'gemm': K.gemm, 'outlook_fwd': K.outlook_fwd, 'outlook_bwd': K.outlook_bwd, 'tlce': K.tlce_fwd_bwd}
+
+    def wrap(name, work):
+        fn = orig[name]
+
+        def inner(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **kw)
+            e1.record()
+            rec[name].append((e0, e1, work(*a, **kw)))
+            return out
+        return inner
+
+    es = 2 if bf16 else 4
+    K.gemm = wrap('gemm', lambda a, b, M, N, Kd, **kw: 2.0 * M * N * Kd)
+    K.outlook_fwd = wrap('outlook_fwd', lambda v, lg, *a, **kw: (2 * v.numel() + lg.numel()) * es)
+    K.outlook_bwd = wrap('outlook_bwd', lambda v, lg, *a, **kw: (3 * v.numel() + 2 * lg.numel()) * es)
+    K.tlce_fwd_bwd = wrap('tlce', lambda xc, xa, *a, **kw: xa.numel() * (2 * es + 4))
+    try:
+        train_step(x, t)
+        torch.cuda.synchronize()
+    finally:
+        K.gemm, K.outlook_fwd, K.outlook_bwd, K.tlce_fwd_bwd = orig['gemm'], orig['outlook_fwd'], orig['outlook_bwd'], orig['tlce']
+
+    def agg(name):
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in rec[name])
+        work = sum(w for _, _, w in rec[name])
+        return ms, work, len(rec[name])
+
+    gms, gflop, gn = agg('gemm')
+    tf = gflop / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
+    roof = {'kernel': 'gemm_tc_kernel (tcgen05) over all Linear/patchify GEMMs of one step', 'bound': 'tensor',
+            'achieved': round(tf, 1), 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+            'frac': round(tf / peaks['bf16_tflops_sustained'], 4), 'traffic': None, 'launches_per_step': gn,
+            'ms_per_step': round(gms, 3), 'peak_source': peaks['src'] + ' (sustained cuBLAS bf16)'}
+    extra = {}
+    fms, fby, fn_ = agg('outlook_fwd')
+    bms, bby, _ = agg('outlook_bwd')
+    if fms + bms > 0:
+        gbs = (fby + bby) / ((fms + bms) * 1e-3) / 1e9
+        extra['roofline_outlook'] = {'kernel': 'OutlookAttention core fwd+bwd', 'bound': 'hbm', 'achieved': round(gbs, 1),
+                                     'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(gbs / peaks['hbm_gbs'], 4),
+                                     'traffic': None, 'layers': fn_, 'ms_per_step': round(fms + bms, 3)}
+    tms, tby, _ = agg('tlce')
+    if tms > 0:
+        gbs = tby / (tms * 1e-3) / 1e9
+        extra['roofline_tlce'] = {'kernel': 'TokenLabelCrossEntropy fused fwd+bwd', 'bound': 'hbm', 'achieved': round(gbs, 1),
+                                  'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(gbs / peaks['hbm_gbs'], 4),
+                                  'traffic': None, 'ms_per_step': round(tms, 3)}
+    return roof, extra
+
+
+if __name__ == '__main__':
+    main()

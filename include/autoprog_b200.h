@@ -139,9 +139,13 @@ int apb_gelu_bwd(const void* x, const void* dy, void* dx, long long n, int dtype
  * (timm create_optimizer('adamw') + 4 x ModelEmaV2.update, main_prog.py:1019-1033)
  * p,g,m,v fp32 [n]; ema: array (device) of n_ema fp32 pointers, decay: host array of n_ema floats (<= 8);
  * shadow: optional bf16 copy of the updated parameters (NULL to skip). */
-int apb_adamw_ema(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                  float eps, float weight_decay, float bias_corr1, float bias_corr2, float* const* ema_ptrs_host,
-                  const float* decay_host, int n_ema, void* shadow_bf16, apb_stream_t stream);
+int apb_adamw_ema(float* p, const float* g, float* m, float* v, long long n, const float* hyper_dev, float beta1,
+                  float beta2, float eps, float weight_decay, float* const* ema_ptrs_host, const float* decay_host,
+                  int n_ema, void* shadow_bf16, apb_stream_t stream);
+/* hyper_dev: DEVICE array {lr, 1-beta1^t, sqrt(1-beta2^t)} so that a captured CUDA graph replays with fresh values. */
+
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches evidence) */
+long long apb_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -278,7 +278,8 @@ def test_misc_elementwise_and_optimizer():
         opt.step()
         for e, d in zip(ref_emas, decays):
             e.mul_(d).add_(ref_p.detach(), alpha=1 - d)
-        K.adamw_ema(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.05, 1 - 0.9 ** step, 1 - 0.999 ** step, emas, decays, shadow)
+        hyper = torch.tensor([1e-3, 1 - 0.9 ** step, (1 - 0.999 ** step) ** 0.5], device=dev)
+        K.adamw_ema(p, g, m, v, hyper, 0.9, 0.999, 1e-8, 0.05, emas, decays, shadow)
     assert rel(p, ref_p) < 1e-6 and rel(emas[0], ref_emas[0]) < 1e-6 and rel(emas[1], ref_emas[1]) < 1e-6
     assert torch.equal(shadow, p.bfloat16())
 
