@@ -16,10 +16,10 @@ _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 SIGNATURES = {
     'apb_last_error': (C.c_char_p, []),
     'apb_abi_version': (_i, []),
-    'apb_outlook_fwd_simt': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
-    'apb_outlook_bwd_simt': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
-    'apb_outlook_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
-    'apb_outlook_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    'apb_outlook_fwd_simt': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    'apb_outlook_bwd_simt': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    'apb_outlook_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    'apb_outlook_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     'apb_tlce_workspace_floats': (_ll, [_i, _i]),
     'apb_tlce_fwd_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     'apb_scale_by_scalar': (_i, [_vp, _vp, _ll, _vp, _i, _vp]),

@@ -6,14 +6,14 @@ int apb_outlook_fwd_mma(const void* v, const void* logits, void* y, int B, int H
 int apb_outlook_bwd_mma(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
                         int heads, float scale, cudaStream_t st);
 
-int apb_outlook_fwd(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int dtype,
-                    apb_stream_t stream) {
-  return apb_outlook_fwd_simt(v, logits, y, B, H, W, heads, scale, dtype, stream);
+int apb_outlook_fwd(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int lpitch,
+                    int dtype, apb_stream_t stream) {
+  return apb_outlook_fwd_simt(v, logits, y, B, H, W, heads, scale, lpitch, dtype, stream);
 }
 
 int apb_outlook_bwd(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
-                    int heads, float scale, int dtype, apb_stream_t stream) {
-  return apb_outlook_bwd_simt(v, logits, dy, dv, dlogits, B, H, W, heads, scale, dtype, stream);
+                    int heads, float scale, int lpitch, int dtype, apb_stream_t stream) {
+  return apb_outlook_bwd_simt(v, logits, dy, dv, dlogits, B, H, W, heads, scale, lpitch, dtype, stream);
 }
 
 int apb_mhsa_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, int heads, float scale, cudaStream_t st);

@@ -70,21 +70,27 @@ __global__ void flip_in_box_kernel(const T* __restrict__ x, T* __restrict__ y, i
 }
 
 // ---- patchify: [B,H,W,C] -> [B*(H/p)*(W/p), p*p*C], K order (kh,kw,c); floor semantics (conv stride p, no padding)
-template <typename T, bool INVERSE>
+// One thread moves VEC contiguous channels (16 bytes when C allows); the (kw, c) run of a patch row is contiguous
+// on both sides, so accesses are fully coalesced.
+template <typename T, int VEC, bool INVERSE>
 __global__ void patchify_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int H, int W, int C, int p, int hp,
                                 int wp) {
-  const long long n = (long long)B * hp * wp * p * p * C;
+  const int cv = C / VEC;
+  const long long n = (long long)B * hp * wp * p * p * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C);
-    long long r = idx / C;
+    const int c = (int)(idx % cv) * VEC;
+    long long r = idx / cv;
     const int kw = (int)(r % p); r /= p;
     const int kh = (int)(r % p); r /= p;
     const int pj = (int)(r % wp); r /= wp;
     const int pi = (int)(r % hp);
     const int b = (int)(r / hp);
     const size_t img = (((size_t)b * H + (pi * p + kh)) * W + (pj * p + kw)) * C + c;
-    if (INVERSE) dst[img] = src[idx];
-    else dst[idx] = src[img];
+    const size_t row = (size_t)(idx / cv) * C + c;
+    const T* s = INVERSE ? src + row : src + img;
+    T* d = INVERSE ? dst + img : dst + row;
+    if (VEC * sizeof(T) == 16) *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(s);
+    else *d = *s;
   }
 }
 
@@ -270,9 +276,20 @@ int apb_patchify(const void* x, void* rows, int B, int H, int W, int C, int p, i
   APB_CHECK_ARG(p > 0 && H >= p && W >= p, APB_ERR_SHAPE, "patchify: H=%d W=%d p=%d", H, W, p);
   const int hp = H / p, wp = W / p;
   const long long n = (long long)B * hp * wp * p * p * C;
+  const bool al = (((uintptr_t)x | (uintptr_t)rows) & 15) == 0;
+  if (dtype == APB_F32 && C % 4 == 0 && al) {
+    patchify_kernel<float, 4, false><<<ew_grid(n / 4), EW_THREADS, 0, st>>>((const float*)x, (float*)rows, B, H, W, C, p, hp, wp);
+    APB_LAUNCH_CHECK("patchify");
+    return 0;
+  }
+  if (dtype == APB_BF16 && C % 8 == 0 && al) {
+    patchify_kernel<bf16, 8, false><<<ew_grid(n / 8), EW_THREADS, 0, st>>>((const bf16*)x, (bf16*)rows, B, H, W, C, p, hp, wp);
+    APB_LAUNCH_CHECK("patchify");
+    return 0;
+  }
   DISPATCH_T(dtype, "patchify",
-             (patchify_kernel<float, false><<<ew_grid(n), EW_THREADS, 0, st>>>((const float*)x, (float*)rows, B, H, W, C, p, hp, wp)),
-             (patchify_kernel<bf16, false><<<ew_grid(n), EW_THREADS, 0, st>>>((const bf16*)x, (bf16*)rows, B, H, W, C, p, hp, wp)));
+             (patchify_kernel<float, 1, false><<<ew_grid(n), EW_THREADS, 0, st>>>((const float*)x, (float*)rows, B, H, W, C, p, hp, wp)),
+             (patchify_kernel<bf16, 1, false><<<ew_grid(n), EW_THREADS, 0, st>>>((const bf16*)x, (bf16*)rows, B, H, W, C, p, hp, wp)));
   return 0;
 }
 
@@ -286,9 +303,20 @@ int apb_unpatchify(const void* rows, void* x, int B, int H, int W, int C, int p,
     DISPATCH_T(dtype, "unpatchify_zero", (zero_kernel<float><<<ew_grid(nimg), EW_THREADS, 0, st>>>((float*)x, nimg)),
                (zero_kernel<bf16><<<ew_grid(nimg), EW_THREADS, 0, st>>>((bf16*)x, nimg)));
   }
+  const bool al = (((uintptr_t)x | (uintptr_t)rows) & 15) == 0;
+  if (dtype == APB_F32 && C % 4 == 0 && al) {
+    patchify_kernel<float, 4, true><<<ew_grid(n / 4), EW_THREADS, 0, st>>>((const float*)rows, (float*)x, B, H, W, C, p, hp, wp);
+    APB_LAUNCH_CHECK("unpatchify");
+    return 0;
+  }
+  if (dtype == APB_BF16 && C % 8 == 0 && al) {
+    patchify_kernel<bf16, 8, true><<<ew_grid(n / 8), EW_THREADS, 0, st>>>((const bf16*)rows, (bf16*)x, B, H, W, C, p, hp, wp);
+    APB_LAUNCH_CHECK("unpatchify");
+    return 0;
+  }
   DISPATCH_T(dtype, "unpatchify",
-             (patchify_kernel<float, true><<<ew_grid(n), EW_THREADS, 0, st>>>((const float*)rows, (float*)x, B, H, W, C, p, hp, wp)),
-             (patchify_kernel<bf16, true><<<ew_grid(n), EW_THREADS, 0, st>>>((const bf16*)rows, (bf16*)x, B, H, W, C, p, hp, wp)));
+             (patchify_kernel<float, 1, true><<<ew_grid(n), EW_THREADS, 0, st>>>((const float*)rows, (float*)x, B, H, W, C, p, hp, wp)),
+             (patchify_kernel<bf16, 1, true><<<ew_grid(n), EW_THREADS, 0, st>>>((const bf16*)rows, (bf16*)x, B, H, W, C, p, hp, wp)));
   return 0;
 }
 

@@ -127,14 +127,27 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TC* __restrict__ dy, 
   }
 }
 
-// out[c] (+)= sum_r part[r][c]   (fixed order -> deterministic)
-__global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ part, int nparts, int C,
-                                                              float* __restrict__ out, int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f;
-  for (int r = 0; r < nparts; ++r) s += part[(size_t)r * C + c];
-  out[c] = accumulate ? out[c] + s : s;
+// out[c] (+)= sum_r part[r][c]   (fixed order -> deterministic).  block = 32 columns x 8 row phases;
+// blockIdx.y selects one of up to two (partials, output) pairs so dgamma and dbeta share a launch.
+__global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ part0, float* __restrict__ out0,
+                                                              const float* __restrict__ part1, float* __restrict__ out1,
+                                                              int nparts, int C, int accumulate) {
+  __shared__ float s[8][33];
+  const float* part = blockIdx.y == 0 ? part0 : part1;
+  float* out = blockIdx.y == 0 ? out0 : out1;
+  const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (c < C)
+    for (int r = ph; r < nparts; r += 8) acc += part[(size_t)r * C + c];
+  s[ph][lane] = acc;
+  __syncthreads();
+  if (ph == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s[k][lane];
+    out[c] = accumulate ? out[c] + t : t;
+  }
 }
 
 // column sums of a [rows, C] matrix: out[c] = sum_r a[r][c]; two-stage, deterministic.
@@ -162,7 +175,7 @@ __global__ void __launch_bounds__(256) colsum_stage1_kernel(const T* __restrict_
 
 }  // namespace
 
-#define LN_GRID_BWD (148 * 4)
+#define LN_GRID_BWD (148 * 4)   // persistent CTAs of the backward kernel (<= this many partial rows)
 
 long long apb_ln_bwd_workspace_floats(int C) { return 2LL * LN_GRID_BWD * C; }
 
@@ -237,8 +250,7 @@ int apb_ln_bwd(const void* dy, const void* xs, const float* mean, const float* r
 #undef LN_BWD
 #undef LN_BWD_NV
   APB_LAUNCH_CHECK("ln_bwd");
-  colsum_partials_kernel<<<ceil_div(C, 256), 256, 0, st>>>(pg, grid, C, dgamma, accumulate);
-  colsum_partials_kernel<<<ceil_div(C, 256), 256, 0, st>>>(pb, grid, C, dbeta, accumulate);
+  colsum_partials_kernel<<<dim3(ceil_div(C, 32), 2), 256, 0, st>>>(pg, dgamma, pb, dbeta, grid, C, accumulate);
   APB_LAUNCH_CHECK("ln_bwd_reduce");
   return 0;
 }
@@ -259,7 +271,7 @@ int apb_colsum(const void* a, long long rows, int C, float* out, int accumulate,
   if (dtype == APB_F32) colsum_stage1_kernel<float><<<grid, 256, 0, st>>>((const float*)a, rows, C, workspace, rows_per_cta);
   else colsum_stage1_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)a, rows, C, workspace, rows_per_cta);
   APB_LAUNCH_CHECK("colsum_stage1");
-  colsum_partials_kernel<<<ceil_div(C, 256), 256, 0, st>>>(workspace, parts, C, out, accumulate);
+  colsum_partials_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, st>>>(workspace, out, nullptr, nullptr, parts, C, accumulate);
   APB_LAUNCH_CHECK("colsum_stage2");
   return 0;
 }

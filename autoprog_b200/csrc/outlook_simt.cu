@@ -7,7 +7,9 @@
 //
 // Layouts (all contiguous):
 //   v, y, dy, dv : [B, H, W, heads*32]            (NHWC, channel = head*32 + c)
-//   logits, dlog : [B, h, w, heads*81]            (h=ceil(H/2), w=ceil(W/2); channel = head*81 + P*9 + Q)
+//   logits, dlog : [B, h, w, lpitch]              (h=ceil(H/2), w=ceil(W/2); channel = head*81 + P*9 + Q;
+//                                                  lpitch >= heads*81, the tail columns are padding: read never,
+//                                                  written as zeros by the backward)
 // Work unit: a "quad" = the 2x2 output pixels (2i..2i+1, 2j..2j+1) of one head, owned by one warp,
 // lane = channel.  The quad needs the 5x5 pixel patch around it and the <=4 windows (i+a, j+b).
 #include "common.cuh"
@@ -19,7 +21,7 @@ constexpr int HD = 32;  // head dim, fixed by every VOLO variant (models/volo.py
 // softmax of the 9x9 logits of up to 4 windows into per-warp shared memory sA[4][81]
 template <typename T>
 __device__ __forceinline__ void quad_softmax(const T* __restrict__ logits, float* sA, int b, int i, int j, int head,
-                                             int h, int w, int heads, float scale, int lane) {
+                                             int h, int w, int lpitch, float scale, int lane) {
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -28,7 +30,7 @@ __device__ __forceinline__ void quad_softmax(const T* __restrict__ logits, float
       float* dst = sA + (a * 2 + bb) * 81;
       if (wi < h && wj < w) {
         if (lane < 9) {
-          const T* src = logits + (((size_t)b * h + wi) * w + wj) * (heads * 81) + head * 81 + lane * 9;
+          const T* src = logits + (((size_t)b * h + wi) * w + wj) * lpitch + head * 81 + lane * 9;
           float e[9], m = -INFINITY;
 #pragma unroll
           for (int q = 0; q < 9; ++q) { e[q] = to_f(src[q]) * scale; m = fmaxf(m, e[q]); }
@@ -65,7 +67,7 @@ __device__ __forceinline__ void load_patch(const T* __restrict__ src, float (&p)
 template <typename T, bool TRANS>
 __global__ void __launch_bounds__(128) outlook_gather_kernel(const T* __restrict__ src, const T* __restrict__ logits,
                                                              T* __restrict__ out, int B, int H, int W, int heads,
-                                                             int h, int w, float scale) {
+                                                             int h, int w, int lpitch, float scale) {
   __shared__ float sA_all[4][4 * 81];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* sA = sA_all[warp];
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(128) outlook_gather_kernel(const T* __restrict
     const int i = (int)(r % h);
     const int b = (int)(r / h);
     __syncwarp();
-    quad_softmax<T>(logits, sA, b, i, j, head, h, w, heads, scale, lane);
+    quad_softmax<T>(logits, sA, b, i, j, head, h, w, lpitch, scale, lane);
     float p[5][5];
     load_patch<T>(src, p, b, i, j, head, H, W, C, lane);
 #pragma unroll
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(128) outlook_gather_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(128) outlook_dlogits_kernel(const T* __restrict__ v, const T* __restrict__ logits,
                                                               const T* __restrict__ dy, T* __restrict__ dlogits,
-                                                              int B, int H, int W, int heads, int h, int w,
+                                                              int B, int H, int W, int heads, int h, int w, int lpitch,
                                                               float scale) {
   __shared__ float sD_all[4][81];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -142,8 +144,9 @@ __global__ void __launch_bounds__(128) outlook_dlogits_kernel(const T* __restric
         if (lane == 0) sD[P * 9 + Q] = s;
       }
     __syncwarp();
+    const size_t win = (((size_t)b * h + i) * w + j) * lpitch;
     if (lane < 9) {
-      const size_t base = (((size_t)b * h + i) * w + j) * (heads * 81) + head * 81 + lane * 9;
+      const size_t base = win + head * 81 + lane * 9;
       float e[9], m = -INFINITY;
 #pragma unroll
       for (int q = 0; q < 9; ++q) { e[q] = to_f(logits[base + q]) * scale; m = fmaxf(m, e[q]); }
@@ -156,6 +159,8 @@ __global__ void __launch_bounds__(128) outlook_dlogits_kernel(const T* __restric
       for (int q = 0; q < 9; ++q) { e[q] *= inv; dot = fmaf(e[q], sD[lane * 9 + q], dot); }
 #pragma unroll
       for (int q = 0; q < 9; ++q) dlogits[base + q] = from_f<T>(scale * e[q] * (sD[lane * 9 + q] - dot));
+    } else if (head == 0 && lane - 9 < lpitch - heads * 81) {
+      dlogits[win + heads * 81 + (lane - 9)] = from_f<T>(0.f);   // padding columns (lpitch - heads*81 <= 7)
     }
   }
 }
@@ -172,41 +177,44 @@ int grid_for(long long units) {
 
 template <typename T>
 static int outlook_fwd_simt_t(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale,
-                              cudaStream_t st) {
+                              int lpitch, cudaStream_t st) {
   const int h = (H + 1) / 2, w = (W + 1) / 2;
   outlook_gather_kernel<T, false><<<grid_for((long long)B * h * w * heads), 128, 0, st>>>(
-      (const T*)v, (const T*)logits, (T*)y, B, H, W, heads, h, w, scale);
+      (const T*)v, (const T*)logits, (T*)y, B, H, W, heads, h, w, lpitch, scale);
   APB_LAUNCH_CHECK("outlook_fwd_simt");
   return 0;
 }
 
 template <typename T>
 static int outlook_bwd_simt_t(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H,
-                              int W, int heads, float scale, cudaStream_t st) {
+                              int W, int heads, float scale, int lpitch, cudaStream_t st) {
   const int h = (H + 1) / 2, w = (W + 1) / 2;
   const int g = grid_for((long long)B * h * w * heads);
-  outlook_gather_kernel<T, true><<<g, 128, 0, st>>>((const T*)dy, (const T*)logits, (T*)dv, B, H, W, heads, h, w, scale);
+  outlook_gather_kernel<T, true><<<g, 128, 0, st>>>((const T*)dy, (const T*)logits, (T*)dv, B, H, W, heads, h, w, lpitch, scale);
   APB_LAUNCH_CHECK("outlook_dv_simt");
   outlook_dlogits_kernel<T><<<g, 128, 0, st>>>((const T*)v, (const T*)logits, (const T*)dy, (T*)dlogits, B, H, W,
-                                                heads, h, w, scale);
+                                                heads, h, w, lpitch, scale);
   APB_LAUNCH_CHECK("outlook_dlogits_simt");
   return 0;
 }
 
+#define OUTLOOK_ARG_CHECK(name)                                                                                   \
+  APB_CHECK_ARG(B > 0 && H > 0 && W > 0 && heads > 0, APB_ERR_SHAPE, name ": bad shape");                         \
+  APB_CHECK_ARG(dtype == APB_F32 || dtype == APB_BF16, APB_ERR_DTYPE, name ": dtype %d", dtype);                  \
+  APB_CHECK_ARG(lpitch >= heads * 81 && lpitch < heads * 81 + 8, APB_ERR_ARG, name ": logits pitch %d for %d heads", lpitch, heads)
+
 int apb_outlook_fwd_simt(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale,
-                         int dtype, apb_stream_t stream) {
+                         int lpitch, int dtype, apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
-  APB_CHECK_ARG(B > 0 && H > 0 && W > 0 && heads > 0, APB_ERR_SHAPE, "outlook_fwd: bad shape");
-  APB_CHECK_ARG(dtype == APB_F32 || dtype == APB_BF16, APB_ERR_DTYPE, "outlook_fwd: dtype %d", dtype);
-  if (dtype == APB_F32) return outlook_fwd_simt_t<float>(v, logits, y, B, H, W, heads, scale, st);
-  return outlook_fwd_simt_t<bf16>(v, logits, y, B, H, W, heads, scale, st);
+  OUTLOOK_ARG_CHECK("outlook_fwd");
+  if (dtype == APB_F32) return outlook_fwd_simt_t<float>(v, logits, y, B, H, W, heads, scale, lpitch, st);
+  return outlook_fwd_simt_t<bf16>(v, logits, y, B, H, W, heads, scale, lpitch, st);
 }
 
 int apb_outlook_bwd_simt(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
-                         int heads, float scale, int dtype, apb_stream_t stream) {
+                         int heads, float scale, int lpitch, int dtype, apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
-  APB_CHECK_ARG(B > 0 && H > 0 && W > 0 && heads > 0, APB_ERR_SHAPE, "outlook_bwd: bad shape");
-  APB_CHECK_ARG(dtype == APB_F32 || dtype == APB_BF16, APB_ERR_DTYPE, "outlook_bwd: dtype %d", dtype);
-  if (dtype == APB_F32) return outlook_bwd_simt_t<float>(v, logits, dy, dv, dlogits, B, H, W, heads, scale, st);
-  return outlook_bwd_simt_t<bf16>(v, logits, dy, dv, dlogits, B, H, W, heads, scale, st);
+  OUTLOOK_ARG_CHECK("outlook_bwd");
+  if (dtype == APB_F32) return outlook_bwd_simt_t<float>(v, logits, dy, dv, dlogits, B, H, W, heads, scale, lpitch, st);
+  return outlook_bwd_simt_t<bf16>(v, logits, dy, dv, dlogits, B, H, W, heads, scale, lpitch, st);
 }

@@ -39,12 +39,14 @@ def _st() -> int:
 
 # ------------------------------------------------------------------ outlook attention core
 def outlook_fwd(v: torch.Tensor, logits: torch.Tensor, heads: int, scale: float, simt: bool = False) -> torch.Tensor:
+    """logits [B,h,w,lpitch] with heads*81 <= lpitch < heads*81+8 (tail = padding)."""
     B, H, W, Cc = v.shape
     assert Cc == heads * 32, 'OutlookAttention kernels are built for head_dim 32'
-    assert logits.shape == (B, (H + 1) // 2, (W + 1) // 2, heads * 81) and logits.dtype == v.dtype
+    lpitch = logits.shape[-1]
+    assert logits.shape[:3] == (B, (H + 1) // 2, (W + 1) // 2) and logits.dtype == v.dtype
     y = torch.empty_like(v)
     fn = lib().apb_outlook_fwd_simt if simt else lib().apb_outlook_fwd
-    check(fn(_p(v), _p(logits), _p(y), B, H, W, heads, scale, dt(v), _st()), 'outlook_fwd')
+    check(fn(_p(v), _p(logits), _p(y), B, H, W, heads, scale, lpitch, dt(v), _st()), 'outlook_fwd')
     return y
 
 
@@ -53,7 +55,7 @@ def outlook_bwd(v, logits, dy, heads: int, scale: float, simt: bool = False) -> 
     dv = torch.empty_like(v)
     dl = torch.empty_like(logits)
     fn = lib().apb_outlook_bwd_simt if simt else lib().apb_outlook_bwd
-    check(fn(_p(v), _p(logits), _p(dy), _p(dv), _p(dl), B, H, W, heads, scale, dt(v), _st()), 'outlook_bwd')
+    check(fn(_p(v), _p(logits), _p(dy), _p(dv), _p(dl), B, H, W, heads, scale, logits.shape[-1], dt(v), _st()), 'outlook_bwd')
     return dv, dl
 
 

@@ -68,6 +68,7 @@ def invalidate_derived_caches() -> None:
     """Called by optimizers that update parameters through raw pointers (no autograd version bump): drops every cached
     re-laid-out / cast copy except the shadows the optimizer itself keeps fresh."""
     _CONVW.clear()
+    _PADW.clear()
     for k in [k for k, v in _WCACHE.items() if not v[3]]:
         del _WCACHE[k]
 
@@ -382,6 +383,26 @@ class _BlockBase(torch.autograd.Function):
         return dn2, dw1, db1, dw2, db2
 
 
+_PADW = {}
+
+
+def wcast_pad_rows(p: torch.Tensor, dtype: torch.dtype, rows: int) -> torch.Tensor:
+    """cast copy of a [N, K] weight (or [N] bias) zero-padded to `rows` rows; refreshed when the parameter changes."""
+    if rows == p.shape[0]:
+        return wcast(p, dtype) if p.dim() == 2 else p.detach()
+    key = (id(p), rows, dtype)
+    ent = _PADW.get(key)
+    if ent is not None and ent[0] == p._version and ent[1] == p.data_ptr():
+        return ent[2]
+    t = torch.zeros((rows,) + tuple(p.shape[1:]), device=p.device, dtype=dtype)
+    K.check(K.lib().apb_cast(p.detach().contiguous().data_ptr(), t.data_ptr(), p.numel(), K.dt(p), K._CODES[dtype],
+                             torch.cuda.current_stream().cuda_stream), 'cast(pad)')
+    if ent is None:
+        weakref.finalize(p, _PADW.pop, key, None)
+    _PADW[key] = (p._version, p.data_ptr(), t)
+    return t
+
+
 class OutlookerFn(_BlockBase):
     """Outlooker.forward (models/volo.py:140-144) with OutlookAttention.forward (:77-103) and Mlp.forward (:161-167)."""
 
@@ -394,11 +415,16 @@ class OutlookerFn(_BlockBase):
         xs, n1, mu1, rstd1 = K.ln_fwd(_c(x), n1w.detach(), n1b.detach(), eps, cdt, r=None if r_in is None else _c(r_in),
                                       rs=rs_in, rows_per_sample=rps)
         xs = xs if xs is not None else _c(x)
-        cv, ca, cp, c1, c2 = (wcast(t, cdt) for t in (wv, wa, wp, w1, w2))
+        cv, cp, c1, c2 = (wcast(t, cdt) for t in (wv, wp, w1, w2))
+        # bf16: pad the 81*heads logit columns to a multiple of 8 so the GEMMs around the core stay on the TMA path
+        nl = wa.shape[0]
+        nlp = (nl + 7) // 8 * 8 if cdt == BF16 else nl
+        ca = wcast_pad_rows(wa, cdt, nlp)
+        ba_p = wcast_pad_rows(ba, F32, nlp)
         n1f = _flat(n1)
         v = _lin_fwd(n1f, cv, None).reshape(B, H, W, Cc)
         pooled = K.avgpool2_fwd(n1)
-        lg = _lin_fwd(_flat(pooled), ca, ba.detach()).reshape(B, pooled.shape[1], pooled.shape[2], -1)
+        lg = _lin_fwd(_flat(pooled), ca, ba_p).reshape(B, pooled.shape[1], pooled.shape[2], -1)
         y = K.outlook_fwd(v, lg, heads, scale)
         o = _lin_fwd(_flat(y), cp, bp.detach()).reshape(B, H, W, Cc)
         x1, n2, mu2, rstd2 = K.ln_fwd(xs, n2w.detach(), n2b.detach(), eps, cdt, r=o, rs=rs_blk, rows_per_sample=rps)
@@ -407,14 +433,14 @@ class OutlookerFn(_BlockBase):
         ctx.save_for_backward(xs, mu1, rstd1, n1, v, pooled, lg, y, x1, mu2, rstd2, n2, u, hdn, cv, ca, cp, c1, c2,
                               n1w.detach(), n2w.detach(), rs_in if rs_in is not None else x.new_empty(0),
                               rs_blk if rs_blk is not None else x.new_empty(0))
-        ctx.meta = (heads, scale, r_in is not None, rs_in is not None, rs_blk is not None)
+        ctx.meta = (heads, scale, r_in is not None, rs_in is not None, rs_blk is not None, nl)
         return x1, z.reshape(B, H, W, Cc)
 
     @staticmethod
     def backward(ctx, dx1_out, dz):
         (xs, mu1, rstd1, n1, v, pooled, lg, y, x1, mu2, rstd2, n2, u, hdn, cv, ca, cp, c1, c2, n1w, n2w, rs_in,
          rs_blk) = ctx.saved_tensors
-        heads, scale, has_r, has_rs_in, has_rs_blk = ctx.meta
+        heads, scale, has_r, has_rs_in, has_rs_blk, nl = ctx.meta
         B, H, W, Cc = xs.shape
         rps = H * W
         cdt = n1.dtype
@@ -427,6 +453,7 @@ class OutlookerFn(_BlockBase):
         dv, dlg = K.outlook_bwd(v, lg, dy.reshape(xs.shape), heads, scale)
         dn1, dwv, _ = _lin_bwd(_flat(dv), _flat(n1), cv, need_db=False)
         dpooled, dwa, dba = _lin_bwd(_flat(dlg), _flat(pooled), ca)
+        dwa, dba = dwa[:nl], dba[:nl]                      # drop the padding rows
         dn1 = K.avgpool2_bwd(dpooled.reshape(pooled.shape), H, W, accumulate_into=dn1.reshape(xs.shape))
         dxs, dr, dn1w, dn1b = K.ln_bwd(dn1, xs, mu1, rstd1, n1w, dres=dx1, want_dr=has_r,
                                        rs=rs_in if has_rs_in else None, rows_per_sample=rps)

@@ -35,13 +35,15 @@ int apb_abi_version(void);
  * `_simt` = fp32-exact CUDA-core path (parity mode); the un-suffixed entry picks the tensor-core bf16 kernel
  * for APB_BF16 and the SIMT kernel for APB_F32. */
 int apb_outlook_fwd_simt(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale,
-                         int dtype, apb_stream_t stream);
+                         int lpitch, int dtype, apb_stream_t stream);
 int apb_outlook_bwd_simt(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H,
-                         int W, int heads, float scale, int dtype, apb_stream_t stream);
-int apb_outlook_fwd(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int dtype,
-                    apb_stream_t stream);
+                         int W, int heads, float scale, int lpitch, int dtype, apb_stream_t stream);
+int apb_outlook_fwd(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int lpitch,
+                    int dtype, apb_stream_t stream);
 int apb_outlook_bwd(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
-                    int heads, float scale, int dtype, apb_stream_t stream);
+                    int heads, float scale, int lpitch, int dtype, apb_stream_t stream);
+/* lpitch: elements between consecutive windows in logits/dlogits, heads*81 <= lpitch < heads*81+8.  The bf16 path
+ * pads 486 -> 488 so the producing / consuming GEMMs satisfy TMA's 16-byte row pitch; backward zero-fills the pad. */
 
 /* ---- TokenLabelCrossEntropy forward + gradient in one pass  (loss/cross_entropy.py:136-156, :30-36)
  * x_cls [B,C], x_aux [B,N,C] (dtype); target fp32 [B,C,2+N] (target_is_3d=1) or [B,C] (0);

@@ -45,6 +45,28 @@ def test_outlook_core(shape, dtype, simt):
     assert torch.equal(dv, dv2) and torch.equal(dl, dl2)
 
 
+@pytest.mark.parametrize('dtype', DT)
+def test_outlook_core_padded_logit_pitch(dtype):
+    """bf16 path pads the 81*heads logit columns to a multiple of 8 (TMA row pitch); pad is ignored / zero-filled."""
+    dev = need_gpu()
+    B, H, W, heads = 2, 9, 8, 6
+    torch.manual_seed(9)
+    h, w = (H + 1) // 2, (W + 1) // 2
+    v = q(torch.randn(B, H, W, heads * 32), dtype)
+    lg = q(torch.randn(B, h, w, heads * 81) * 2, dtype)
+    dy = q(torch.randn(B, H, W, heads * 32), dtype)
+    lgp = torch.full((B, h, w, heads * 81 + 2), 1e4, dtype=torch.float64)
+    lgp[..., :heads * 81] = lg
+    s = 32 ** -0.5
+    y_ref = O.outlook_core(v, lg, heads, s)
+    dv_ref, dl_ref = O.outlook_core_bwd(v, lg, dy, heads, s)
+    for simt in (True, False):
+        y = K.outlook_fwd(v.to(dev, dtype), lgp.to(dev, dtype), heads, s, simt=simt)
+        dv, dl = K.outlook_bwd(v.to(dev, dtype), lgp.to(dev, dtype), dy.to(dev, dtype), heads, s, simt=simt)
+        assert rel(y, y_ref) < tol(dtype) and rel(dv, dv_ref) < tol(dtype) and rel(dl[..., :heads * 81], dl_ref) < tol(dtype)
+        assert float(dl[..., heads * 81:].float().abs().max()) == 0.0
+
+
 def test_outlook_module_golden():
     """kernel path == the reference module's output stored by oracle/gen_golden.py"""
     dev = need_gpu()
