@@ -9,18 +9,24 @@
 //   trans_a = 0: A is [M,K] row-major  (K-major operand)    1: A is [K,M] row-major (MN-major operand)
 //   trans_b = 0: B is [N,K] row-major  (K-major operand)    1: B is [K,N] row-major (MN-major operand)
 //
-// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2..5 = epilogue
-// (one TMEM lane quarter each).  Tile 128 x BN x 64, 3-stage mbarrier ring, 2 CTAs per SM so one CTA's epilogue
-// overlaps the other's main loop (K is short on this path: 3..18 k-blocks).  split_k > 1 writes fp32 partial tiles
-// [split][M][N] that the caller reduces in fixed order (deterministic wgrad).
+// PERSISTENT kernel, one CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
+// issuer, warps 2..17 = epilogue (four warps per TMEM lane quarter, each taking 32 of the tile's 128 columns: the
+// CUDA-core epilogue math needs that many warps in flight to hide its own latency).
+// Tile 128 x 128 x 64, 4-stage smem ring, TWO accumulator stages in TMEM: the epilogue of tile i overlaps the main
+// loop of tile i+1.  Epilogue warps stage their 32 x 64 sub-tile in 128B-swizzled shared memory and write it with a TMA
+// store (cp.async.bulk.tensor ... bulk_group): fully coalesced, asynchronous, and M/N tails are clipped by the TMA unit.  K is short on this path (3..18 k-blocks), so the CUDA-core epilogue (not the tensor pipe) is the
+// critical resource: GELU uses a 1.5e-7-accurate erf (Abramowitz-Stegun 7.1.26: one MUFU.RCP + one MUFU.EX2).
+// split_k > 1 writes fp32 partial tiles [split][M][N] that the caller reduces in fixed order (deterministic wgrad).
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
 
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 3;
-constexpr int NTHREADS = 192;
+constexpr int BM = 128, BK = 64;
+constexpr int EPI_WARPS = 16;
+constexpr int NTHREADS = 64 + EPI_WARPS * 32;
+constexpr int ACC_STAGES = 2;
 
 struct TcParams {
   void* C;
@@ -30,7 +36,9 @@ struct TcParams {
   int a_mn, b_mn;       // operand majors (1 = MN-major)
   int epilogue;         // 0 none, 1 gelu, 2 dgelu, 4 split-k partial
   int out_f32;
-  int kb_per_split;     // k-blocks per blockIdx.z
+  int kb_per_split;     // k-blocks per split
+  int splits;
+  int tiles_m, tiles_n;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -40,6 +48,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -94,46 +105,80 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): cdf = Phi(x), pdf_e = exp(-x^2/2)
+__device__ __forceinline__ void phi_fast(float x, float& cdf, float& e) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
+  e = exp2f(-z * z * 1.4426950408889634f);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float half_tail = 0.5f * poly * t * e;          // 0.5 * (1 - erf(z))
+  cdf = x >= 0.f ? 1.f - half_tail : half_tail;
+}
+__device__ __forceinline__ float gelu_f(float x) {
+  float cdf, e;
+  phi_fast(x, cdf, e);
+  return x * cdf;
+}
 __device__ __forceinline__ float dgelu_f(float x) {
-  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, e;
+  phi_fast(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
-template <int BN>
-__global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a,
-                                                             const __grid_constant__ CUtensorMap tma_b, TcParams p) {
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// 16-byte chunk `chunk` (0..7) of row `row` (0..31) inside a 32-row x 128-byte staging box with the 128B TMA swizzle
+__device__ __forceinline__ uint8_t* stg128(uint8_t* stg, int row, int chunk) {
+  return stg + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+// 16-byte chunk `chunk` (0..3) of row `row` inside a 32-row x 64-byte staging box with the 64B TMA swizzle
+__device__ __forceinline__ uint8_t* stg64(uint8_t* stg, int row, int chunk) {
+  return stg + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                             const __grid_constant__ CUtensorMap tma_b,
+                                                             const __grid_constant__ CUtensorMap tma_c,
+                                                             const __grid_constant__ CUtensorMap tma_x, TcParams p) {
   constexpr uint32_t A_BYTES = BM * BK * 2;   // 16 KB
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  constexpr uint32_t STG_BYTES = 4096 + 2048;   // per epilogue warp: a 32 x 128 B box (C) + a 32 x 64 B box (aux)
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + EPI_WARPS * STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int total_kb = (p.K + BK - 1) / BK;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int kb1 = min(total_kb, kb0 + p.kb_per_split);
-  const int nkb = kb1 - kb0;   // >= 1 by construction on the host
+  const int n_items = p.tiles_m * p.tiles_n * p.splits;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_c) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_x) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -144,24 +189,30 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
   if (warp == 0) {
     // ===================== TMA producer (one elected lane) =====================
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        if (i >= STAGES) mbar_wait(&empty_bar[s], ((i / STAGES) - 1) & 1);
-        uint8_t* sa = smem + s * STAGE_BYTES;
-        uint8_t* sb = sa + A_BYTES;
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        const int k0 = (kb0 + i) * BK;
-        if (!p.a_mn) {
-          tma_load_2d(sa, &tma_a, &full_bar[s], k0, m0);                 // box {64 k, 128 m}
-        } else {
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int z = item % p.splits, t = item / p.splits;
+        const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
+        const int kb0 = z * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tma_a, &full_bar[s], k0, m0);                 // box {64 k, 128 m}
+          } else {
 #pragma unroll
-          for (int h = 0; h < BM / 64; ++h) tma_load_2d(sa + h * (BK * 128), &tma_a, &full_bar[s], m0 + h * 64, k0);  // box {64 m, 64 k}
-        }
-        if (!p.b_mn) {
-          tma_load_2d(sb, &tma_b, &full_bar[s], k0, n0);                 // box {64 k, BN n}
-        } else {
+            for (int h = 0; h < BM / 64; ++h) tma_load_2d(sa + h * (BK * 128), &tma_a, &full_bar[s], m0 + h * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tma_b, &full_bar[s], k0, n0);                 // box {64 k, BN n}
+          } else {
 #pragma unroll
-          for (int h = 0; h < BN / 64; ++h) tma_load_2d(sb + h * (BK * 128), &tma_b, &full_bar[s], n0 + h * 64, k0);
+            for (int h = 0; h < BN / 64; ++h) tma_load_2d(sb + h * (BK * 128), &tma_b, &full_bar[s], n0 + h * 64, k0);
+          }
         }
       }
     }
@@ -172,132 +223,134 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_tc_kernel(const __grid_const
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
       const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        mbar_wait(&full_bar[s], (i / STAGES) & 1);
+      uint32_t it = 0, ai = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ai) {
+        const int z = item % p.splits;
+        const int kb0 = z * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+        const uint32_t as = ai % ACC_STAGES;
+        mbar_wait(&tempty_bar[as], ((ai / ACC_STAGES) & 1) ^ 1);      // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+        const uint32_t tacc = tmem_base + as * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
-          const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16(tacc, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);   // frees the smem stage once the MMAs above have read it
         }
-        umma_commit(&empty_bar[s]);   // frees the smem stage once the MMAs above have read it
+        umma_commit(&tfull_bar[as]);    // accumulator of this tile complete
       }
-      umma_commit(tmem_full_bar);     // accumulator complete
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
-    const int row = m0 + quarter * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const bool row_ok = row < p.M;
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    const int cg = (warp - 2) >> 2;               // which 32-column slice of the tile
+    uint8_t* stg0 = stg_base + (warp - 2) * STG_BYTES;   // C box   (bf16: 32 x 64 B, fp32: 32 x 128 B)
+    uint8_t* stg1 = stg0 + 4096;                         // aux box (bf16 32 x 64 B)
+    uint32_t ai = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ai) {
+      const int z = item % p.splits, t = item / p.splits;
+      const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
+      const uint32_t as = ai % ACC_STAGES;
+      mbar_wait(&tfull_bar[as], (ai / ACC_STAGES) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
-      const int col0 = n0 + c * 32;
-      if (!row_ok || col0 >= p.N) continue;
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(cg * 32), r);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&tempty_bar[as]);                                  // accumulator stage free for tile i+2
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous TMA stores have drained the staging boxes
+      }
+      __syncwarp();
+      const int cb = n0 + cg * 32;                // first column of this warp's sub-tile
+      const int rb = m0 + quarter * 32;           // first row
+      if (cb >= p.N || rb >= p.M) continue;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      const int ncol = min(32, p.N - col0);
-      if (p.epilogue == 4) {
-        float* dst = reinterpret_cast<float*>(p.C) + ((size_t)blockIdx.z * p.M + row) * p.N + col0;
-        if (ncol == 32 && (p.N & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < ncol; ++j) dst[j] = v[j];
-        }
-        continue;
-      }
       if (p.bias != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < ncol) v[j] += __ldg(p.bias + col0 + j);
+        for (int j = 0; j < 32; j += 4)
+          if (cb + j < p.N) {                     // N % 8 == 0 on this path
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
       }
-      const size_t off = (size_t)row * p.N + col0;
+      if (p.epilogue == 2) {
+        // dGELU: fetch the pre-activation sub-tile coalesced (4 lanes per 64-byte row), then read the own row back
+        const bf16* ax = reinterpret_cast<const bf16*>(p.aux);
+#pragma unroll
+        for (int itr = 0; itr < 4; ++itr) {
+          const int rr = itr * 8 + (lane >> 2), ch = lane & 3;
+          uint4 val = make_uint4(0u, 0u, 0u, 0u);
+          if (rb + rr < p.M && cb + ch * 8 < p.N) val = *reinterpret_cast<const uint4*>(ax + (size_t)(rb + rr) * p.N + cb + ch * 8);
+          *reinterpret_cast<uint4*>(stg64(stg1, rr, ch)) = val;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint4 pk = *reinterpret_cast<const uint4*>(stg64(stg1, lane, ch));
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            v[ch * 8 + 2 * tt] *= dgelu_f(__bfloat162float(h2[tt].x));
+            v[ch * 8 + 2 * tt + 1] *= dgelu_f(__bfloat162float(h2[tt].y));
+          }
+        }
+        __syncwarp();
+      } else if (p.epilogue == 1) {
+        // GELU: store the rounded pre-activation (what backward re-reads) and activate that rounded value
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint4 pk;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) h2[tt] = __floats2bfloat162_rn(v[ch * 8 + 2 * tt], v[ch * 8 + 2 * tt + 1]);
+          *reinterpret_cast<uint4*>(stg64(stg1, lane, ch)) = pk;
+#pragma unroll
+          for (int tt = 0; tt < 4; ++tt) {
+            v[ch * 8 + 2 * tt] = gelu_f(__bfloat162float(h2[tt].x));
+            v[ch * 8 + 2 * tt + 1] = gelu_f(__bfloat162float(h2[tt].y));
+          }
+        }
+      }
       if (p.out_f32) {
-        float* dst = reinterpret_cast<float*>(p.C) + off;
-        if (p.epilogue == 1) {
-          float* ax = reinterpret_cast<float*>(p.aux) + off;
-          for (int j = 0; j < ncol; ++j) { ax[j] = v[j]; v[j] = gelu_f(v[j]); }
-        } else if (p.epilogue == 2) {
-          const float* ax = reinterpret_cast<const float*>(p.aux) + off;
-          for (int j = 0; j < ncol; ++j) v[j] *= dgelu_f(ax[j]);
-        }
-        if (ncol == 32 && (p.N & 3) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < ncol; ++j) dst[j] = v[j];
-        }
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<float4*>(stg128(stg0, lane, ch)) = make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
       } else {
-        bf16* dst = reinterpret_cast<bf16*>(p.C) + off;
-        const bool vec = (ncol == 32) && ((p.N & 7) == 0);
-        if (p.epilogue == 1) {
-          bf16* ax = reinterpret_cast<bf16*>(p.aux) + off;
-          if (vec) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+        for (int ch = 0; ch < 4; ++ch) {
+          uint4 pk;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-              for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-              *reinterpret_cast<uint4*>(ax + j) = pk;
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {   // GELU of the ROUNDED pre-activation (what backward will re-read)
-                v[j + 2 * t] = gelu_f(__bfloat162float(h2[t].x));
-                v[j + 2 * t + 1] = gelu_f(__bfloat162float(h2[t].y));
-              }
-            }
-          } else {
-            for (int j = 0; j < ncol; ++j) {
-              const bf16 pre = __float2bfloat16_rn(v[j]);
-              ax[j] = pre;
-              v[j] = gelu_f(__bfloat162float(pre));
-            }
-          }
-        } else if (p.epilogue == 2) {
-          const bf16* ax = reinterpret_cast<const bf16*>(p.aux) + off;
-          if (vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 pk = *reinterpret_cast<const uint4*>(ax + j);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                v[j + 2 * t] *= dgelu_f(__bfloat162float(h2[t].x));
-                v[j + 2 * t + 1] *= dgelu_f(__bfloat162float(h2[t].y));
-              }
-            }
-          } else {
-            for (int j = 0; j < ncol; ++j) v[j] *= dgelu_f(__bfloat162float(ax[j]));
-          }
+          for (int tt = 0; tt < 4; ++tt) h2[tt] = __floats2bfloat162_rn(v[ch * 8 + 2 * tt], v[ch * 8 + 2 * tt + 1]);
+          *reinterpret_cast<uint4*>(stg64(stg0, lane, ch)) = pk;
         }
-        if (vec) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) h2[t] = __floats2bfloat162_rn(v[j + 2 * t], v[j + 2 * t + 1]);
-            *reinterpret_cast<uint4*>(dst + j) = pk;
-          }
-        } else {
-          for (int j = 0; j < ncol; ++j) dst[j] = __float2bfloat16_rn(v[j]);
-        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tma_c, stg0, cb, rb, z);
+        if (p.epilogue == 1) tma_store_3d(&tma_x, stg1, cb, rb, 0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -340,17 +393,51 @@ int make_map(CUtensorMap* map, const void* base, long long rows, long long cols,
   return 0;
 }
 
-template <int BN>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int splits, cudaStream_t st) {
-  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 128;
+// output tensor [splits, M, N] row-major; box {32 columns, 32 rows, 1}: fp32 -> 128 B rows / 128B swizzle, bf16 -> 64 B / 64B
+int make_map_out(CUtensorMap* map, const void* base, bool f32, long long M, long long N, long long splits) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) { apb_set_error("gemm_tc: cuTensorMapEncodeTiled entry point unavailable"); return APB_ERR_UNSUPPORTED; }
+  const cuuint64_t esz = f32 ? 4 : 2;
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)splits};
+  cuuint64_t strides[2] = {(cuuint64_t)N * esz, (cuuint64_t)N * (cuuint64_t)M * esz};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    apb_set_error("gemm_tc: cuTensorMapEncodeTiled(out) failed (%d) M=%lld N=%lld splits=%lld base=%p", (int)r, M, N, splits, base);
+    return APB_ERR_ARG;
+  }
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mx, TcParams p, int splits,
+           cudaStream_t st) {
+  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + EPI_WARPS * (4096 + 2048) + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { apb_set_error("gemm_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
-  dim3 grid(ceil_div(p.M, BM), ceil_div(p.N, BN), splits);
-  gemm_tc_kernel<BN><<<grid, NTHREADS, smem, st>>>(ma, mb, p);
+  p.tiles_m = ceil_div(p.M, BM);
+  p.tiles_n = ceil_div(p.N, BN);
+  p.splits = splits;
+  const long long items = (long long)p.tiles_m * p.tiles_n * splits;
+  const int grid = (int)(items < num_sms() ? items : num_sms());
+  gemm_tc_kernel<BN, STAGES><<<grid, NTHREADS, smem, st>>>(ma, mb, mc, mx, p);
   APB_LAUNCH_CHECK("gemm_tc");
   return 0;
 }
@@ -392,7 +479,15 @@ int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* 
   p.out_f32 = (out_dtype == APB_F32) ? 1 : 0;
   p.kb_per_split = kb_per;
   if (splits > 1) APB_CHECK_ARG(out_dtype == APB_F32, APB_ERR_DTYPE, "gemm_tc: split-K partials are fp32");
-  return launch<128>(ma, mb, p, splits, st);
+  APB_CHECK_ARG(!(p.out_f32 && (epilogue == 1 || epilogue == 2)), APB_ERR_UNSUPPORTED, "gemm_tc: GELU epilogues write bf16");
+  APB_CHECK_ARG(N % 8 == 0, APB_ERR_UNSUPPORTED, "gemm_tc: N=%d must be a multiple of 8 (TMA store pitch)", N);
+  APB_CHECK_ARG(aux == nullptr || ((uintptr_t)aux & 15) == 0, APB_ERR_ARG, "gemm_tc: aux must be 16-byte aligned");
+  CUtensorMap mc, mx;
+  rc = make_map_out(&mc, C, p.out_f32 != 0, M, N, splits);
+  if (rc) return rc;
+  rc = make_map_out(&mx, (epilogue == 1) ? aux : C, (epilogue == 1) ? false : (p.out_f32 != 0), M, N, (epilogue == 1) ? 1 : splits);
+  if (rc) return rc;
+  return launch<128, 4>(ma, mb, mc, mx, p, splits, st);
 }
 
 // number of K splits the wgrad-shaped GEMM should use to fill the GPU (host helper for the binding)

@@ -301,7 +301,7 @@ def measure_rooflines(train_step, x, t, K, torch, B, bf16):
         return inner
 
     es = 2 if bf16 else 4
-    K.gemm = wrap('gemm', lambda a, b, M, N, Kd, **kw: 2.0 * M * N * Kd)
+    K.gemm = wrap('gemm', lambda a, b, M, N, Kd, **kw: (2.0 * M * N * Kd, (M, N, Kd, int(kw.get('trans_a', False)), int(kw.get('trans_b', False)), kw.get('epilogue', 0))))
     K.outlook_fwd = wrap('outlook_fwd', lambda v, lg, *a, **kw: (2 * v.numel() + lg.numel()) * es)
     K.outlook_bwd = wrap('outlook_bwd', lambda v, lg, *a, **kw: (3 * v.numel() + 2 * lg.numel()) * es)
     K.tlce_fwd_bwd = wrap('tlce', lambda xc, xa, *a, **kw: xa.numel() * (2 * es + 4))
@@ -310,6 +310,15 @@ def measure_rooflines(train_step, x, t, K, torch, B, bf16):
         torch.cuda.synchronize()
     finally:
         K.gemm, K.outlook_fwd, K.outlook_bwd, K.tlce_fwd_bwd = orig['gemm'], orig['outlook_fwd'], orig['outlook_bwd'], orig['tlce']
+
+    if os.environ.get('APB_BENCH_GEMM_TABLE'):
+        tab = {}
+        for e0, e1, (w, key) in rec['gemm']:
+            t = tab.setdefault(key, [0, 0.0, 0.0])
+            t[0] += 1; t[1] += e0.elapsed_time(e1); t[2] += w
+        for key, (n, ms, w) in sorted(tab.items(), key=lambda kv: -kv[1][1]):
+            print(f'[gemm] M,N,K,ta,tb,epi={key} x{n}: {ms:.3f} ms  {w / ms / 1e9:.0f} TFLOP/s', file=sys.stderr)
+    rec['gemm'] = [(e0, e1, w[0]) for e0, e1, w in rec['gemm']]
 
     def agg(name):
         ms = sum(e0.elapsed_time(e1) for e0, e1, _ in rec[name])
