@@ -175,6 +175,12 @@ __global__ void __launch_bounds__(256) colsum_stage1_kernel(const T* __restrict_
 
 }  // namespace
 
+int ln_bwd_v4_launch(const void* dy, const void* xs, const float* mean, const float* rstd, const float* gamma,
+                     const void* dres, void* dxs, void* dr, const float* rs, int rows_per_sample, float* pg, float* pb,
+                     int grid, long long rows, int C, int sdtype, int cdtype, cudaStream_t st);
+int colsum_v8_launch(const void* a, long long rows, int C, float* part, int rows_per_cta, int parts, int dtype,
+                     cudaStream_t st);
+
 #define LN_GRID_BWD (148 * 4)   // persistent CTAs of the backward kernel (<= this many partial rows)
 
 long long apb_ln_bwd_workspace_floats(int C) { return 2LL * LN_GRID_BWD * C; }
@@ -225,6 +231,16 @@ int apb_ln_bwd(const void* dy, const void* xs, const float* mean, const float* r
   float* pb = workspace + (size_t)LN_GRID_BWD * C;
   const size_t smem = (size_t)8 * 2 * C * sizeof(float);
   const int nv = (C + 31) / 32;
+  {
+    const int handled = ln_bwd_v4_launch(dy, xs, mean, rstd, gamma, dres, dxs, dr, rs, rows_per_sample, pg, pb, grid, rows, C,
+                                         sdtype, cdtype, st);
+    if (handled == 1) {
+      APB_LAUNCH_CHECK("ln_bwd_v4");
+      colsum_partials_kernel<<<dim3(ceil_div(C, 32), 2), 256, 0, st>>>(pg, dgamma, pb, dbeta, grid, C, accumulate);
+      APB_LAUNCH_CHECK("ln_bwd_reduce");
+      return 0;
+    }
+  }
 #define LN_BWD_NV(NV_, TS_, TC_)                                                                                       \
   do {                                                                                                                 \
     cudaFuncSetAttribute(ln_bwd_kernel<NV_, TS_, TC_, TS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
@@ -267,9 +283,11 @@ int apb_colsum(const void* a, long long rows, int C, float* out, int accumulate,
   if (rows <= 0 || C <= 0) return 0;
   const int rows_per_cta = 512;
   const int parts = (int)((rows + rows_per_cta - 1) / rows_per_cta);
-  dim3 grid(ceil_div(C, 32), parts);
-  if (dtype == APB_F32) colsum_stage1_kernel<float><<<grid, 256, 0, st>>>((const float*)a, rows, C, workspace, rows_per_cta);
-  else colsum_stage1_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)a, rows, C, workspace, rows_per_cta);
+  if (colsum_v8_launch(a, rows, C, workspace, rows_per_cta, parts, dtype, st) != 1) {
+    dim3 grid(ceil_div(C, 32), parts);
+    if (dtype == APB_F32) colsum_stage1_kernel<float><<<grid, 256, 0, st>>>((const float*)a, rows, C, workspace, rows_per_cta);
+    else colsum_stage1_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)a, rows, C, workspace, rows_per_cta);
+  }
   APB_LAUNCH_CHECK("colsum_stage1");
   colsum_partials_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, st>>>(workspace, out, nullptr, nullptr, parts, C, accumulate);
   APB_LAUNCH_CHECK("colsum_stage2");

@@ -1,0 +1,196 @@
+// Vectorised, branch-free variants of the LayerNorm backward and column-sum kernels (C % 4 == 0 / C % 8 == 0).
+//
+// The first versions (layernorm.cu) guard every element with `if (c < C)`; ptxas keeps those guards as branches, so
+// the 36 loads of a row were issued one basic block at a time and the kernel sat at 10 % of HBM bandwidth waiting on
+// the long scoreboard (profiles/r1_kernels.md).  Here every lane issues all of a row's 16-byte loads up front
+// (clamped addresses + 0/1 masks instead of branches).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  uint2 u;
+  *reinterpret_cast<__nv_bfloat162*>(&u.x) = __floats2bfloat162_rn(v.x, v.y);
+  *reinterpret_cast<__nv_bfloat162*>(&u.y) = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// NG groups of 4 consecutive channels per lane (group id = k*32 + lane)
+template <int NG, typename TS, typename TC>
+__global__ void __launch_bounds__(256) ln_bwd_v4_kernel(const TC* __restrict__ dy, const TS* __restrict__ xs,
+                                                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                        const float* __restrict__ gamma, const TS* __restrict__ dres,
+                                                        TS* __restrict__ dxs, TC* __restrict__ dr,
+                                                        const float* __restrict__ rs, int rows_per_sample,
+                                                        float* __restrict__ part_g, float* __restrict__ part_b,
+                                                        long long rows, int C) {
+  extern __shared__ float sm[];  // [nwarp][2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int ngroups = C >> 2;
+  int off[NG];
+  float okf[NG];
+  float4 gam[NG], ag[NG], ab[NG];
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+    const int g = k * 32 + lane;
+    const bool ok = g < ngroups;
+    off[k] = (ok ? g : 0) * 4;
+    okf[k] = ok ? 1.f : 0.f;
+    gam[k] = ld4(gamma + off[k]);
+    ag[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float invC = 1.f / (float)C;
+  for (long long row = (long long)blockIdx.x * nwarp + warp; row < rows; row += (long long)gridDim.x * nwarp) {
+    const size_t base = (size_t)row * C;
+    float4 xv[NG], dv[NG], rv[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {      // all loads of the row in flight before any use
+      xv[k] = ld4(xs + base + off[k]);
+      dv[k] = ld4(dy + base + off[k]);
+      rv[k] = dres != nullptr ? ld4(dres + base + off[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float mu = mean[row], rs_ = rstd[row];
+    const float bs = (rs != nullptr) ? rs[row / rows_per_sample] : 1.f;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      const float m = okf[k];
+      xv[k].x = (xv[k].x - mu) * rs_; xv[k].y = (xv[k].y - mu) * rs_; xv[k].z = (xv[k].z - mu) * rs_; xv[k].w = (xv[k].w - mu) * rs_;
+      dv[k].x *= m; dv[k].y *= m; dv[k].z *= m; dv[k].w *= m;
+      ag[k].x = fmaf(dv[k].x, xv[k].x, ag[k].x); ag[k].y = fmaf(dv[k].y, xv[k].y, ag[k].y);
+      ag[k].z = fmaf(dv[k].z, xv[k].z, ag[k].z); ag[k].w = fmaf(dv[k].w, xv[k].w, ag[k].w);
+      ab[k].x += dv[k].x; ab[k].y += dv[k].y; ab[k].z += dv[k].z; ab[k].w += dv[k].w;
+      dv[k].x *= gam[k].x; dv[k].y *= gam[k].y; dv[k].z *= gam[k].z; dv[k].w *= gam[k].w;   // g = dy * gamma
+      s1 += (dv[k].x + dv[k].y) + (dv[k].z + dv[k].w);
+      s2 += fmaf(dv[k].x, xv[k].x, dv[k].y * xv[k].y) + fmaf(dv[k].z, xv[k].z, dv[k].w * xv[k].w);
+    }
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      float4 d;
+      d.x = fmaf(rs_, dv[k].x - s1 - xv[k].x * s2, rv[k].x);
+      d.y = fmaf(rs_, dv[k].y - s1 - xv[k].y * s2, rv[k].y);
+      d.z = fmaf(rs_, dv[k].z - s1 - xv[k].z * s2, rv[k].z);
+      d.w = fmaf(rs_, dv[k].w - s1 - xv[k].w * s2, rv[k].w);
+      if (okf[k] != 0.f) {
+        st4(dxs + base + off[k], d);
+        if (dr != nullptr) st4(dr + base + off[k], make_float4(bs * d.x, bs * d.y, bs * d.z, bs * d.w));
+      }
+    }
+  }
+  float* sg = sm + (size_t)warp * 2 * C;
+#pragma unroll
+  for (int k = 0; k < NG; ++k)
+    if (okf[k] != 0.f) {
+      st4(sg + off[k], ag[k]);
+      st4(sg + C + off[k], ab[k]);
+    }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float tg = 0.f, tb = 0.f;
+    for (int w2 = 0; w2 < nwarp; ++w2) { tg += sm[(size_t)w2 * 2 * C + c]; tb += sm[(size_t)w2 * 2 * C + C + c]; }
+    part_g[(size_t)blockIdx.x * C + c] = tg;
+    part_b[(size_t)blockIdx.x * C + c] = tb;
+  }
+}
+
+// column sums, stage 1: lane = 8 consecutive columns (16-byte loads for bf16), warp = 256 columns, warps stride the rows
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_v8_kernel(const T* __restrict__ a, long long rows, int C,
+                                                        float* __restrict__ part, int rows_per_cta) {
+  __shared__ float s[8][256 + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + lane * 8;
+  const bool ok = c0 < C;
+  const int cc = ok ? c0 : 0;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = min(rows, r0 + (long long)rows_per_cta);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  long long r = r0 + warp;
+  for (; r + 24 < r1; r += 32) {        // 4 rows in flight per warp
+    float4 lo[4], hi[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      lo[u] = ld4(a + (size_t)(r + 8 * u) * C + cc);
+      hi[u] = ld4(a + (size_t)(r + 8 * u) * C + cc + 4);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc[0] += lo[u].x; acc[1] += lo[u].y; acc[2] += lo[u].z; acc[3] += lo[u].w;
+      acc[4] += hi[u].x; acc[5] += hi[u].y; acc[6] += hi[u].z; acc[7] += hi[u].w;
+    }
+  }
+  for (; r < r1; r += 8) {
+    const float4 lo = ld4(a + (size_t)r * C + cc), hi = ld4(a + (size_t)r * C + cc + 4);
+    acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w;
+    acc[4] += hi.x; acc[5] += hi.y; acc[6] += hi.z; acc[7] += hi.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[warp][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s[k][threadIdx.x];
+    part[(size_t)blockIdx.y * C + c] = t;
+  }
+}
+
+}  // namespace
+
+// returns 1 if handled, 0 if the caller must use the scalar kernel, <0 / >1 on error
+int ln_bwd_v4_launch(const void* dy, const void* xs, const float* mean, const float* rstd, const float* gamma,
+                     const void* dres, void* dxs, void* dr, const float* rs, int rows_per_sample, float* pg, float* pb,
+                     int grid, long long rows, int C, int sdtype, int cdtype, cudaStream_t st) {
+  if ((C & 3) != 0 || C > 1024) return 0;
+  const uintptr_t al = (uintptr_t)dy | (uintptr_t)xs | (uintptr_t)gamma | (uintptr_t)dres | (uintptr_t)dxs | (uintptr_t)dr;
+  if (al & 15) return 0;
+  const int ng = (C / 4 + 31) / 32;
+  const size_t smem = (size_t)8 * 2 * C * sizeof(float);
+#define V4(NG_, TS_, TC_)                                                                                             \
+  do {                                                                                                                \
+    cudaFuncSetAttribute(ln_bwd_v4_kernel<NG_, TS_, TC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    ln_bwd_v4_kernel<NG_, TS_, TC_><<<grid, 256, smem, st>>>((const TC_*)dy, (const TS_*)xs, mean, rstd, gamma,        \
+                                                             (const TS_*)dres, (TS_*)dxs, (TC_*)dr, rs, rows_per_sample, \
+                                                             pg, pb, rows, C);                                        \
+  } while (0)
+#define V4_T(TS_, TC_)                  \
+  do {                                  \
+    if (ng <= 1) V4(1, TS_, TC_);       \
+    else if (ng <= 2) V4(2, TS_, TC_);  \
+    else if (ng <= 3) V4(3, TS_, TC_);  \
+    else if (ng <= 4) V4(4, TS_, TC_);  \
+    else if (ng <= 6) V4(6, TS_, TC_);  \
+    else V4(8, TS_, TC_);               \
+  } while (0)
+  if (sdtype == APB_F32 && cdtype == APB_F32) V4_T(float, float);
+  else if (sdtype == APB_F32 && cdtype == APB_BF16) V4_T(float, bf16);
+  else if (sdtype == APB_BF16 && cdtype == APB_BF16) V4_T(bf16, bf16);
+  else return 0;
+#undef V4_T
+#undef V4
+  return 1;
+}
+
+int colsum_v8_launch(const void* a, long long rows, int C, float* part, int rows_per_cta, int parts, int dtype,
+                     cudaStream_t st) {
+  if ((C & 7) != 0 || ((uintptr_t)a & 15)) return 0;
+  dim3 grid(ceil_div(C, 256), parts);
+  if (dtype == APB_F32) colsum_v8_kernel<float><<<grid, 256, 0, st>>>((const float*)a, rows, C, part, rows_per_cta);
+  else if (dtype == APB_BF16) colsum_v8_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)a, rows, C, part, rows_per_cta);
+  else return 0;
+  return 1;
+}

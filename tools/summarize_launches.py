@@ -1,14 +1,16 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel count / total / share."""
-import csv, sys, collections, re
+import csv, sys, re
 rows = list(csv.reader(open(sys.argv[1], errors='ignore')))
 hdr = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
 H = rows[hdr]; ki, vi, ui = H.index('Kernel Name'), H.index('Metric Value'), H.index('Metric Unit')
-agg = collections.OrderedDict()
+agg = {}
 for r in rows[hdr + 1:]:
     if len(r) <= vi: continue
-    name = re.sub(r'\(.*', '', r[ki]); name = re.sub(r'<.*', '', name)[:60]
+    n = r[ki]
+    m = re.search(r'(?:anonymous namespace)::(\w+)(<[^>]*>)?', n)
+    name = (m.group(1) + (m.group(2) or '')) if m else re.sub(r'^void ', '', n).split('(')[0][:70]
     v = float(r[vi].replace(',', '')); u = r[ui]
-    us = v / 1000 if u in ('ns', 'nsecond') else (v if u.startswith('us') else v * 1000 if u.startswith('ms') else v)
+    us = v / 1000 if u.startswith('ns') else v
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += us
 tot = sum(a[1] for a in agg.values())
 print(f'total {tot/1000:.3f} ms over {sum(a[0] for a in agg.values())} launches')
