@@ -1,18 +1,29 @@
 // dtype dispatch for ops that have both a tensor-core bf16 kernel and a CUDA-core fp32 kernel.
 #include "common.cuh"
 
-int apb_outlook_fwd_mma(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale,
+int apb_outlook_fwd_mma(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int lpitch,
                         cudaStream_t st);
 int apb_outlook_bwd_mma(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
-                        int heads, float scale, cudaStream_t st);
+                        int heads, float scale, int lpitch, cudaStream_t st);
 
+// bf16 -> tensor-core kernels (outlook_mma.cu); fp32, or shapes whose band does not fit shared memory -> SIMT kernels
 int apb_outlook_fwd(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int lpitch,
                     int dtype, apb_stream_t stream) {
+  if (dtype == APB_BF16 && B > 0 && H > 0 && W > 0 && heads > 0 && lpitch >= heads * 81 && lpitch < heads * 81 + 8 &&
+      (((uintptr_t)v | (uintptr_t)y) & 15) == 0) {
+    const int rc = apb_outlook_fwd_mma(v, logits, y, B, H, W, heads, scale, lpitch, APB_STREAM(stream));
+    if (rc != APB_ERR_UNSUPPORTED) return rc;
+  }
   return apb_outlook_fwd_simt(v, logits, y, B, H, W, heads, scale, lpitch, dtype, stream);
 }
 
 int apb_outlook_bwd(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
                     int heads, float scale, int lpitch, int dtype, apb_stream_t stream) {
+  if (dtype == APB_BF16 && B > 0 && H > 0 && W > 0 && heads > 0 && lpitch >= heads * 81 && lpitch < heads * 81 + 8 &&
+      (((uintptr_t)v | (uintptr_t)dy | (uintptr_t)dv) & 15) == 0) {
+    const int rc = apb_outlook_bwd_mma(v, logits, dy, dv, dlogits, B, H, W, heads, scale, lpitch, APB_STREAM(stream));
+    if (rc != APB_ERR_UNSUPPORTED) return rc;
+  }
   return apb_outlook_bwd_simt(v, logits, dy, dv, dlogits, B, H, W, heads, scale, lpitch, dtype, stream);
 }
 
