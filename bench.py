@@ -254,7 +254,13 @@ def main():
     roof = None
     extra = {}
     if rank == 0:
-        roof, extra = measure_rooflines(train_step, x_dev, t_dev, K, torch, B, bf16)
+        # rank-local extra step: no collective may be issued here (the other ranks do not take part)
+        if world > 1:
+            with net.no_sync():
+                roof, extra = measure_rooflines(train_step, x_dev, t_dev, K, torch, B, bf16)
+        else:
+            roof, extra = measure_rooflines(train_step, x_dev, t_dev, K, torch, B, bf16)
+    barrier()
 
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
