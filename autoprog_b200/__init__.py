@@ -10,7 +10,7 @@ There is no CPU or eager fallback.
 """
 from .registry import create_model, register_model, list_models, is_model  # noqa: F401
 from .ops import autocast  # noqa: F401
-from . import volo, submodels  # noqa: F401  (registers volo_d1..d5, model_variant)
+from . import volo, submodels, deit  # noqa: F401  (registers volo_d1..d5, model_variant, deit_*)
 from .volo import VOLO  # noqa: F401
 from .cross_entropy import (SoftTargetCrossEntropy, TokenLabelCrossEntropy, TokenLabelGTCrossEntropy,  # noqa: F401
                             TokenLabelSoftTargetCrossEntropy)

@@ -258,6 +258,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
       const int z = item % p.splits, t = item / p.splits;
       const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
       const uint32_t as = ai % ACC_STAGES;
+      const int cb = n0 + cg * 32;                // first column of this warp's sub-tile
+      const int rb = m0 + quarter * 32;           // first row
+      if (p.epilogue == 2 && cb < p.N && rb < p.M) {
+        // dGELU: fetch the pre-activation sub-tile (coalesced, 4 lanes per 64-byte row) while the MMAs of this tile run
+        const bf16* ax = reinterpret_cast<const bf16*>(p.aux);
+#pragma unroll
+        for (int itr = 0; itr < 4; ++itr) {
+          const int rr = itr * 8 + (lane >> 2), ch = lane & 3;
+          uint4 val = make_uint4(0u, 0u, 0u, 0u);
+          if (rb + rr < p.M && cb + ch * 8 < p.N) val = *reinterpret_cast<const uint4*>(ax + (size_t)(rb + rr) * p.N + cb + ch * 8);
+          *reinterpret_cast<uint4*>(stg64(stg1, rr, ch)) = val;
+        }
+      }
       mbar_wait(&tfull_bar[as], (ai / ACC_STAGES) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t r[32];
@@ -270,8 +283,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous TMA stores have drained the staging boxes
       }
       __syncwarp();
-      const int cb = n0 + cg * 32;                // first column of this warp's sub-tile
-      const int rb = m0 + quarter * 32;           // first row
       if (cb >= p.N || rb >= p.M) continue;
       float v[32];
 #pragma unroll
@@ -285,15 +296,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
           }
       }
       if (p.epilogue == 2) {
-        // dGELU: fetch the pre-activation sub-tile coalesced (4 lanes per 64-byte row), then read the own row back
-        const bf16* ax = reinterpret_cast<const bf16*>(p.aux);
-#pragma unroll
-        for (int itr = 0; itr < 4; ++itr) {
-          const int rr = itr * 8 + (lane >> 2), ch = lane & 3;
-          uint4 val = make_uint4(0u, 0u, 0u, 0u);
-          if (rb + rr < p.M && cb + ch * 8 < p.N) val = *reinterpret_cast<const uint4*>(ax + (size_t)(rb + rr) * p.N + cb + ch * 8);
-          *reinterpret_cast<uint4*>(stg64(stg1, rr, ch)) = val;
-        }
+        // dGELU: the pre-activation sub-tile was prefetched into stg1 above; read the own row back
         __syncwarp();
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
@@ -494,11 +497,19 @@ int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* 
 int apb_gemm_tc_suggest_split(int M, int N, int K) {
   const int tiles = ceil_div(M, BM) * ceil_div(N, 128);
   const int total_kb = (K + BK - 1) / BK;
-  if (tiles >= 148 || total_kb < 8) return 1;
-  int s = (2 * 148 + tiles - 1) / tiles;
-  if (s > total_kb / 4) s = total_kb / 4;
-  if (s < 1) s = 1;
-  if (s > 64) s = 64;
-  int kb_per = (total_kb + s - 1) / s;
-  return (total_kb + kb_per - 1) / kb_per;
+  const int sms = 148;
+  if (tiles >= sms || total_kb < 16) return 1;
+  // choose the split count whose work items fill whole waves of the persistent grid best (>= 8 k-blocks per item)
+  int best = 1;
+  double best_score = 0.0;
+  for (int s = 1; s <= 64 && s * 8 <= total_kb; ++s) {
+    const int kb_per = (total_kb + s - 1) / s;
+    if ((total_kb + kb_per - 1) / kb_per != s) continue;          // not realisable without an empty split
+    const int items = tiles * s;
+    const int waves = (items + sms - 1) / sms;
+    const double eff = (double)items / (waves * sms);             // SM utilisation
+    const double score = eff / (1.0 + 0.02 * s);                  // mild preference for fewer partials to reduce
+    if (score > best_score) { best_score = score; best = s; }
+  }
+  return best;
 }

@@ -2,9 +2,9 @@
 //
 //   reference: nn.Unfold(3,1,2) -> softmax(scale*logits) -> attn @ v -> F.fold          (models/volo.py:83-98)
 //
-// A CTA owns a band of TR window rows of one image (all window columns when they fit, all heads).  It stages the
-// (2TR+3)-row pixel band of v (and dy in the backward) ONCE in shared memory with coalesced 16-byte loads; every
-// window/head unit then is a 16x16x16 mma.sync problem whose operands come straight from that tile:
+// A CTA owns a band of TR window rows of one image (all window columns, all heads).  It stages the (2TR+3)-row pixel
+// band of v (and dy in the backward) ONCE in shared memory with coalesced 16-byte loads; every (window, head) unit
+// then is a 16x16x16 mma.sync problem whose operands come straight from that tile:
 //   forward : out[P][c]  = sum_Q A[P][Q] v[pix(Q)][c]        A = softmax fragment built in registers (warp shuffles)
 //   backward: dA[P][Q]   = <dy[pix(P)], v[pix(Q)]>           ; dlogits = scale * A o (dA - rowsum(A o dA))
 //             dvw[Q][c]  = sum_P A[P][Q] dy[pix(P)][c]       (A^T through movmatrix)
@@ -12,13 +12,14 @@
 // deterministic gather: per head, unit results are staged in shared memory and every output pixel sums the 1/2/4
 // window rows that cover it -- no atomics.  HBM traffic is exactly one read of v / logits (/ dy) and one write of
 // y (/ dv, dlogits); the halo rows re-read by neighbouring bands hit L2.
+// The kernel is issue-bound, so everything loop-invariant (per-lane ldmatrix / staging offsets) is hoisted out of the
+// unit loop and all shared-memory addressing is 32-bit.
 #include "common.cuh"
 
 namespace {
 
 constexpr int HD = 32;
-constexpr int OS = 40;          // fp32 staging row pitch (32 channels + 8 pad: conflict-free 64-bit stores)
-constexpr int NTHREADS = 512;
+constexpr int OS = 40;          // fp32 staging row pitch in floats (32 channels + 8 pad: conflict-free 64-bit stores)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
@@ -39,6 +40,14 @@ __device__ __forceinline__ uint32_t movmatrix_t(uint32_t a) {
   asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
   return d;
 }
+__device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -54,37 +63,41 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 struct Geo {
   int B, H, W, heads, h, w, lpitch;
-  int TR;              // window rows per CTA
+  int TR;              // window rows owned per CTA
   int nWR;             // window rows computed per CTA (TR + 1 halo)
   int PR, PC, Cp;      // staged pixel rows / cols, padded channel pitch (bf16 elements)
   float scale;
 };
 
 // stage pixel rows [y0, y0+PR) x cols [-1, -1+PC) of src[b] (NHWC bf16) into s[PR][PC][Cp]; outside the image -> zeros
+template <int NT>
 __device__ __forceinline__ void stage_band(bf16* s, const bf16* __restrict__ src, const Geo& g, int b, int y0) {
   const int C = g.heads * HD;
-  const int cpr = C / 8;                                   // 16-byte chunks per pixel
-  const int total = g.PR * g.PC * cpr;
-  for (int e = threadIdx.x; e < total; e += NTHREADS) {
-    const int ch = e % cpr;
-    const int px = (e / cpr) % g.PC;
-    const int py = e / (cpr * g.PC);
-    const int y = y0 + py, x = px - 1;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (y >= 0 && y < g.H && x >= 0 && x < g.W)
-      val = *reinterpret_cast<const uint4*>(src + (((size_t)b * g.H + y) * g.W + x) * C + ch * 8);
-    *reinterpret_cast<uint4*>(s + ((size_t)py * g.PC + px) * g.Cp + ch * 8) = val;
+  const int cpr = C >> 3;                                  // 16-byte chunks per pixel
+  const int per_row = g.PC * cpr;
+  const bf16* img = src + (size_t)b * g.H * g.W * C;
+  for (int py = 0; py < g.PR; ++py) {
+    const int y = y0 + py;
+    const bool yok = (y >= 0 && y < g.H);
+    const bf16* grow = img + (size_t)(yok ? y : 0) * g.W * C - C;   // column x = px - 1
+    bf16* srow = s + (size_t)py * g.PC * g.Cp;
+    for (int e = threadIdx.x; e < per_row; e += NT) {
+      const int px = e / cpr, ch = e - px * cpr;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (yok && px >= 1 && px <= g.W) val = *reinterpret_cast<const uint4*>(grow + (size_t)px * C + ch * 8);
+      *reinterpret_cast<uint4*>(srow + px * g.Cp + ch * 8) = val;
+    }
   }
 }
 
 // raw logits of one unit in fragment order: (P=g: Q=2q, 2q+1, 8) and, for g == 0, (P=8: Q=2q, 2q+1, 8)
 struct RawLogits { float e0, e1, e2, f0, f1, f2; };
-__device__ __forceinline__ RawLogits load_logits(const bf16* __restrict__ L, int lane) {
-  const int gi = lane >> 2, q = lane & 3;
+__device__ __forceinline__ RawLogits load_logits(const bf16* __restrict__ L, int gi, int q) {
   RawLogits r;
-  r.e0 = to_f(L[gi * 9 + 2 * q]);
-  r.e1 = to_f(L[gi * 9 + 2 * q + 1]);
-  r.e2 = (q == 0) ? to_f(L[gi * 9 + 8]) : 0.f;
+  const bf16* row = L + gi * 9 + 2 * q;
+  r.e0 = to_f(row[0]);
+  r.e1 = to_f(row[1]);
+  r.e2 = (q == 0) ? to_f(row[8]) : 0.f;
   r.f0 = r.f1 = r.f2 = 0.f;
   if (gi == 0) {
     r.f0 = to_f(L[72 + 2 * q]);
@@ -97,208 +110,247 @@ __device__ __forceinline__ RawLogits load_logits(const bf16* __restrict__ L, int
 // softmax of one unit's 9x9 logits, produced directly in mma fragment layout (fp32, warp shuffles inside each quad).
 //   pf : probabilities in accumulator layout: pf[0][0..1] = (P=g, Q=2q,2q+1), pf[0][2..3] = (P=g+8, same Q),
 //        pf[1][0..1] = (P=g, Q=8+2q, 9+2q), pf[1][2..3] = (P=g+8, ...); rows / cols >= 9 are zero
-__device__ __forceinline__ void softmax_frag(const RawLogits& r, float scale, int lane, float (&pf)[2][4]) {
-  const int gi = lane >> 2, q = lane & 3;
+__device__ __forceinline__ void softmax_frag(const RawLogits& r, float sl2, int gi, int q, float (&pf)[2][4]) {
   const float NEG = -INFINITY;
-  float e0 = r.e0 * scale, e1 = r.e1 * scale;
-  float e2 = (q == 0) ? r.e2 * scale : NEG;
-  float f0 = NEG, f1 = NEG, f2 = NEG;
-  if (gi == 0) {
-    f0 = r.f0 * scale;
-    f1 = r.f1 * scale;
-    if (q == 0) f2 = r.f2 * scale;
-  }
+  float e0 = r.e0 * sl2, e1 = r.e1 * sl2;                 // logits * scale * log2(e)
+  float e2 = (q == 0) ? r.e2 * sl2 : NEG;
+  float f0 = (gi == 0) ? r.f0 * sl2 : NEG, f1 = (gi == 0) ? r.f1 * sl2 : NEG;
+  float f2 = (gi == 0 && q == 0) ? r.f2 * sl2 : NEG;
   const float m0 = quad_max(fmaxf(fmaxf(e0, e1), e2));
-  const float m1 = quad_max(fmaxf(fmaxf(f0, f1), f2));     // -inf for gi != 0
-  e0 = __expf(e0 - m0); e1 = __expf(e1 - m0); e2 = (q == 0) ? __expf(e2 - m0) : 0.f;
-  const float inv0 = 1.f / quad_sum(e0 + e1 + e2);
-  float inv1 = 0.f;
-  if (gi == 0) { f0 = __expf(f0 - m1); f1 = __expf(f1 - m1); f2 = (q == 0) ? __expf(f2 - m1) : 0.f; } else { f0 = f1 = f2 = 0.f; }
+  float m1 = quad_max(fmaxf(fmaxf(f0, f1), f2));
+  m1 = (gi == 0) ? m1 : 0.f;                              // keeps exp2(-inf - m1) = 0 without NaNs
+  e0 = exp2f(e0 - m0); e1 = exp2f(e1 - m0); e2 = exp2f(e2 - m0);
+  f0 = exp2f(f0 - m1); f1 = exp2f(f1 - m1); f2 = exp2f(f2 - m1);
+  const float inv0 = __frcp_rn(quad_sum(e0 + e1 + e2));
   const float s1 = quad_sum(f0 + f1 + f2);
-  if (gi == 0) inv1 = 1.f / s1;
+  const float inv1 = (gi == 0) ? __frcp_rn(s1) : 0.f;
   pf[0][0] = e0 * inv0; pf[0][1] = e1 * inv0; pf[0][2] = f0 * inv1; pf[0][3] = f1 * inv1;
   pf[1][0] = e2 * inv0; pf[1][1] = 0.f;       pf[1][2] = f2 * inv1; pf[1][3] = 0.f;
 }
 
-// smem address (bf16 elements) of pixel-row `idx` (0..15; >= 9 -> zero row) of window (lr, lc) for head `hd`
-__device__ __forceinline__ const bf16* win_row(const bf16* tile, const bf16* zero, const Geo& g, int lr, int lc, int hd, int idx) {
-  if (idx >= 9) return zero;
-  const int py = 2 * lr + idx / 3, px = 2 * lc + idx % 3;
-  return tile + ((size_t)py * g.PC + px) * g.Cp + hd * HD;
+// loop-invariant per-lane geometry
+struct LaneGeo {
+  uint32_t offT;      // byte offset (from the unit's base pixel) of this lane's ldmatrix row for "rows x channels" operands
+  uint32_t offB[2];   // byte offsets of this lane's row for the B operand of dA (n-block 0 / 1)
+  bool zT, zB[2];     // row index >= 9 -> read the zero row instead
+  uint32_t offS;      // byte offset of this lane inside a unit's staging block
+};
+__device__ __forceinline__ uint32_t pix_off(const Geo& g, int idx) { return (uint32_t)(((idx / 3) * g.PC + idx % 3) * g.Cp * 2); }
+__device__ __forceinline__ LaneGeo lane_geo(const Geo& g, int lane) {
+  LaneGeo L;
+  const int mi = lane >> 3, r = lane & 7;
+  const int idxT = (mi & 1) * 8 + r;
+  L.zT = idxT >= 9;
+  L.offT = L.zT ? 0u : pix_off(g, idxT) + (uint32_t)((mi >> 1) * 16);
+#pragma unroll
+  for (int nb = 0; nb < 2; ++nb) {
+    const int idxB = nb * 8 + r;
+    L.zB[nb] = idxB >= 9;
+    L.offB[nb] = L.zB[nb] ? 0u : pix_off(g, idxB) + (uint32_t)(mi * 16);
+  }
+  L.offS = (uint32_t)(((lane >> 2) * OS + 2 * (lane & 3)) * 4);
+  return L;
 }
 
 // res[16 x 32] += Afrag[16 x 16] . rows(tile)[16 x 32]   (B operand through ldmatrix.trans; rows = window pixels)
-__device__ __forceinline__ void mma_rows(float (&acc)[4][4], const uint32_t (&a)[4], const bf16* tile, const bf16* zero,
-                                         const Geo& g, int lr, int lc, int hd, int lane) {
-  const int mi = lane >> 3, r = lane & 7;
-  const bf16* rowp = win_row(tile, zero, g, lr, lc, hd, (mi & 1) * 8 + r);
-  const int coff = (rowp == zero) ? 0 : (mi >> 1) * 8;
+__device__ __forceinline__ void mma_rows(float (&acc)[4][4], const uint32_t (&a)[4], uint32_t unit_base, uint32_t zero_s,
+                                         const LaneGeo& L) {
+  const uint32_t a0 = L.zT ? zero_s : unit_base + L.offT;
+  const uint32_t a1 = L.zT ? zero_s : a0 + 32;           // channels 16..31
+  uint32_t b[4];
+  ldsm_x4_t(b, a0);
+  mma16816(acc[0], a, b[0], b[1]);
+  mma16816(acc[1], a, b[2], b[3]);
+  ldsm_x4_t(b, a1);
+  mma16816(acc[2], a, b[0], b[1]);
+  mma16816(acc[3], a, b[2], b[3]);
+}
+
+// accumulator rows 0..8 -> staging block of the unit ([9][OS] floats)
+__device__ __forceinline__ void stage_unit(uint32_t blk, const float (&acc)[4][4], const LaneGeo& L, int gi) {
+  const uint32_t p = blk + L.offS;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t b[4];
-    ldsm_x4_t(b, smem_u32(rowp + (rowp == zero ? 0 : half * 16) + coff));
-    mma16816(acc[half * 2 + 0], a, b[0], b[1]);
-    mma16816(acc[half * 2 + 1], a, b[2], b[3]);
+  for (int nb = 0; nb < 4; ++nb) sts64(p + nb * 32, acc[nb][0], acc[nb][1]);
+  if (gi == 0) {
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) sts64(p + 8 * OS * 4 + nb * 32, acc[nb][2], acc[nb][3]);
   }
 }
 
-// accumulator rows 0..8 -> staging sOut[unit][9][OS]
-__device__ __forceinline__ void stage_unit(float* sOut, int unit, const float (&acc)[4][4], int lane) {
-  const int gi = lane >> 2, q = lane & 3;
-  float* base = sOut + (size_t)unit * 9 * OS;
-#pragma unroll
-  for (int nb = 0; nb < 4; ++nb) {
-    *reinterpret_cast<float2*>(base + gi * OS + nb * 8 + 2 * q) = make_float2(acc[nb][0], acc[nb][1]);
-    if (gi == 0) *reinterpret_cast<float2*>(base + 8 * OS + nb * 8 + 2 * q) = make_float2(acc[nb][2], acc[nb][3]);
-  }
-}
-
-// fold as a gather: output pixel (ly, lx) of the band (local coords) sums its covering (window, row) entries
-__device__ __forceinline__ void gather_store(const float* sOut, bf16* __restrict__ dst, const Geo& g, int b, int i0, int hd,
-                                             int nWR) {
+// fold as a gather: output pixel (ly, lx) of the band (local coords) sums its covering (window, row) staging entries
+template <int NT>
+__device__ __forceinline__ void gather_store(uint32_t sOut_s, bf16* __restrict__ dst_band, const Geo& g, int rows, int nWR_eff,
+                                             int hd, int ly0, int lx0) {
   const int C = g.heads * HD;
-  const int rows = min(2 * g.TR, g.H - 2 * i0);
-  const int tasks = rows * g.W * 8;                       // 8 threads (4 channels each) per pixel
-  for (int t = threadIdx.x; t < tasks; t += NTHREADS) {
-    const int c4 = (t & 7) * 4;
-    const int lx = (t >> 3) % g.W, ly = (t >> 3) / g.W;
+  const int c4 = (threadIdx.x & 7) * 4;
+  constexpr int S = NT / 8;                                // pixels handled per sweep
+  int ly = ly0, lx = lx0;
+  while (ly < rows) {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      // row: even -> (lr = ly/2, k=1); odd -> (lr=(ly-1)/2, k=2) and (lr=(ly+1)/2, k=0)
-      int lr, ki;
-      if ((ly & 1) == 0) { if (a) continue; lr = ly >> 1; ki = 1; }
-      else { lr = (ly >> 1) + a; ki = a ? 0 : 2; }
-      if (lr >= nWR || i0 + lr >= g.h) continue;
-#pragma unroll
-      for (int bb = 0; bb < 2; ++bb) {
-        int lc, kj;
-        if ((lx & 1) == 0) { if (bb) continue; lc = lx >> 1; kj = 1; }
-        else { lc = (lx >> 1) + bb; kj = bb ? 0 : 2; }
-        if (lc >= g.w) continue;
-        const float4 v4 = *reinterpret_cast<const float4*>(sOut + ((size_t)(lr * g.w + lc) * 9 + ki * 3 + kj) * OS + c4);
-        s.x += v4.x; s.y += v4.y; s.z += v4.z; s.w += v4.w;
+    // rows: even -> (lr = ly/2, ki = 1); odd -> (lr = (ly-1)/2, ki = 2) and (lr = (ly+1)/2, ki = 0); same for columns
+    const int lr0 = ly >> 1, lc0 = lx >> 1;
+    const int ki0 = (ly & 1) ? 2 : 1, kj0 = (lx & 1) ? 2 : 1;
+    const bool r2 = (ly & 1) && (lr0 + 1 < nWR_eff), c2 = (lx & 1) && (lc0 + 1 < g.w);
+    const uint32_t e00 = sOut_s + (uint32_t)((((lr0 * g.w + lc0) * 9 + ki0 * 3 + kj0) * OS + c4) * 4);
+    {
+      const float4 t = lds128(e00);
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    if (c2) {   // window (lr0, lc0+1), kj = 0
+      const float4 t = lds128(e00 + (uint32_t)((9 - kj0) * OS * 4));
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+    }
+    if (r2) {   // window (lr0+1, lc0), ki = 0
+      const uint32_t e10 = e00 + (uint32_t)((g.w * 9 - ki0 * 3) * OS * 4);
+      const float4 t = lds128(e10);
+      s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      if (c2) {
+        const float4 t2 = lds128(e10 + (uint32_t)((9 - kj0) * OS * 4));
+        s.x += t2.x; s.y += t2.y; s.z += t2.z; s.w += t2.w;
       }
     }
     uint2 pk;
     pk.x = pack_bf16(s.x, s.y);
     pk.y = pack_bf16(s.z, s.w);
-    *reinterpret_cast<uint2*>(dst + (((size_t)b * g.H + 2 * i0 + ly) * g.W + lx) * C + hd * HD + c4) = pk;
+    *reinterpret_cast<uint2*>(dst_band + ((size_t)ly * g.W + lx) * C + hd * HD + c4) = pk;
+    lx += S;
+    while (lx >= g.W) { lx -= g.W; ++ly; }
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2) outlook_fwd_mma_kernel(const bf16* __restrict__ v, const bf16* __restrict__ logits,
-                                                                     bf16* __restrict__ y, Geo g) {
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) outlook_fwd_mma_kernel(const bf16* __restrict__ v, const bf16* __restrict__ logits,
+                                                               bf16* __restrict__ y, Geo g) {
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* zero = reinterpret_cast<bf16*>(smraw);                                     // 64 bytes of zeros
   bf16* sV = zero + 32;
-  float* sOut = reinterpret_cast<float*>(sV + (size_t)g.PR * g.PC * g.Cp);
+  const uint32_t tile_bytes = (uint32_t)(g.PR * g.PC * g.Cp * 2);
+  const uint32_t zero_s = smem_u32(zero), sV_s = zero_s + 64, sOut_s = sV_s + tile_bytes;
   const int b = blockIdx.y, i0 = blockIdx.x * g.TR;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = NTHREADS / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int nwarp = NT / 32;
+  const int gi = lane >> 2, q = lane & 3;
   if (threadIdx.x < 32) zero[threadIdx.x] = __float2bfloat16_rn(0.f);
-  stage_band(sV, v, g, b, 2 * i0 - 1);
+  stage_band<NT>(sV, v, g, b, 2 * i0 - 1);
   const int nWR = min(g.nWR, g.h - i0);
   const int units = nWR * g.w;
-  // the logits of a warp's NEXT unit are fetched while the current one is computed (they are the only global loads
-  // inside the unit loop; the prefetch also runs across the per-head barriers)
-  const size_t lrow0 = ((size_t)b * g.h + i0) * g.w;
-  RawLogits nxt = load_logits(logits + (lrow0 + (warp < units ? warp : 0)) * g.lpitch, lane);
+  const LaneGeo L = lane_geo(g, lane);
+  const float sl2 = g.scale * 1.4426950408889634f;
+  const int rows = min(2 * g.TR, g.H - 2 * i0);
+  const int ps = threadIdx.x >> 3;
+  const int ly0 = ps / g.W, lx0 = ps - ly0 * g.W;
+  bf16* ydst = y + ((size_t)b * g.H + 2 * i0) * g.W * (g.heads * HD);
+  const uint32_t row_pitch = (uint32_t)(g.PC * g.Cp * 2);
+  // logits of a warp's NEXT unit are fetched while the current one is computed (the only global loads in the loop)
+  const bf16* lbase = logits + ((size_t)b * g.h + i0) * g.w * g.lpitch;
+  RawLogits nxt = load_logits(lbase + (size_t)(warp < units ? warp : 0) * g.lpitch, gi, q);
   __syncthreads();
   for (int hd = 0; hd < g.heads; ++hd) {
+    int lr = warp / g.w, lc = warp - lr * g.w;
     for (int u = warp; u < units; u += nwarp) {
-      const int lr = u / g.w, lc = u % g.w;
       const RawLogits cur = nxt;
       {
         int nu = u + nwarp, nh = hd;
         if (nu >= units) { nu = warp; ++nh; }
-        if (nh < g.heads && nu < units) nxt = load_logits(logits + (lrow0 + nu) * g.lpitch + nh * 81, lane);
+        if (nh < g.heads && nu < units) nxt = load_logits(lbase + (size_t)nu * g.lpitch + nh * 81, gi, q);
       }
       float pf[2][4];
-      softmax_frag(cur, g.scale, lane, pf);
+      softmax_frag(cur, sl2, gi, q, pf);
       const uint32_t a[4] = {pack_bf16(pf[0][0], pf[0][1]), pack_bf16(pf[0][2], pf[0][3]), pack_bf16(pf[1][0], pf[1][1]),
                              pack_bf16(pf[1][2], pf[1][3])};
       float acc[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-      mma_rows(acc, a, sV, zero, g, lr, lc, hd, lane);
-      stage_unit(sOut, u, acc, lane);
+      const uint32_t ub = sV_s + (uint32_t)(2 * lr) * row_pitch + (uint32_t)((2 * lc * g.Cp + hd * HD) * 2);
+      mma_rows(acc, a, ub, zero_s, L);
+      stage_unit(sOut_s + (uint32_t)(u * 9 * OS * 4), acc, L, gi);
+      lc += nwarp;
+      while (lc >= g.w) { lc -= g.w; ++lr; }
     }
     __syncthreads();
-    gather_store(sOut, y, g, b, i0, hd, nWR);
+    gather_store<NT>(sOut_s, ydst, g, rows, nWR, hd, ly0, lx0);
     __syncthreads();
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) outlook_bwd_mma_kernel(const bf16* __restrict__ v, const bf16* __restrict__ logits,
-                                                                     const bf16* __restrict__ dy, bf16* __restrict__ dv,
-                                                                     bf16* __restrict__ dlogits, Geo g) {
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) outlook_bwd_mma_kernel(const bf16* __restrict__ v, const bf16* __restrict__ logits,
+                                                               const bf16* __restrict__ dy, bf16* __restrict__ dv,
+                                                               bf16* __restrict__ dlogits, Geo g) {
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* zero = reinterpret_cast<bf16*>(smraw);
   bf16* sV = zero + 32;
+  const uint32_t tile_bytes = (uint32_t)(g.PR * g.PC * g.Cp * 2);
   bf16* sG = sV + (size_t)g.PR * g.PC * g.Cp;
-  float* sOut = reinterpret_cast<float*>(sG + (size_t)g.PR * g.PC * g.Cp);
+  const uint32_t zero_s = smem_u32(zero), sV_s = zero_s + 64, sG_s = sV_s + tile_bytes, sOut_s = sG_s + tile_bytes;
   const int b = blockIdx.y, i0 = blockIdx.x * g.TR;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = NTHREADS / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int nwarp = NT / 32;
   const int gi = lane >> 2, q = lane & 3;
   if (threadIdx.x < 32) zero[threadIdx.x] = __float2bfloat16_rn(0.f);
-  stage_band(sV, v, g, b, 2 * i0 - 1);
-  stage_band(sG, dy, g, b, 2 * i0 - 1);
+  stage_band<NT>(sV, v, g, b, 2 * i0 - 1);
+  stage_band<NT>(sG, dy, g, b, 2 * i0 - 1);
   const int nWR = min(g.nWR, g.h - i0);
   const int units = nWR * g.w;
-  const size_t lrow0 = ((size_t)b * g.h + i0) * g.w;
-  RawLogits nxt = load_logits(logits + (lrow0 + (warp < units ? warp : 0)) * g.lpitch, lane);
+  const LaneGeo L = lane_geo(g, lane);
+  const float sl2 = g.scale * 1.4426950408889634f;
+  const int rows = min(2 * g.TR, g.H - 2 * i0);
+  const int ps = threadIdx.x >> 3;
+  const int ly0 = ps / g.W, lx0 = ps - ly0 * g.W;
+  bf16* ddst = dv + ((size_t)b * g.H + 2 * i0) * g.W * (g.heads * HD);
+  const uint32_t row_pitch = (uint32_t)(g.PC * g.Cp * 2);
+  const int npad = g.lpitch - g.heads * 81;
+  const size_t lband = ((size_t)b * g.h + i0) * g.w * g.lpitch;
+  const bf16* lbase = logits + lband;
+  bf16* dlbase = dlogits + lband;
+  RawLogits nxt = load_logits(lbase + (size_t)(warp < units ? warp : 0) * g.lpitch, gi, q);
   __syncthreads();
   for (int hd = 0; hd < g.heads; ++hd) {
+    int lr = warp / g.w, lc = warp - lr * g.w;
     for (int u = warp; u < units; u += nwarp) {
-      const int lr = u / g.w, lc = u % g.w;
-      const size_t lbase = (lrow0 + u) * g.lpitch + hd * 81;
       const RawLogits cur = nxt;
       {
         int nu = u + nwarp, nh = hd;
         if (nu >= units) { nu = warp; ++nh; }
-        if (nh < g.heads && nu < units) nxt = load_logits(logits + (lrow0 + nu) * g.lpitch + nh * 81, lane);
+        if (nh < g.heads && nu < units) nxt = load_logits(lbase + (size_t)nu * g.lpitch + nh * 81, gi, q);
       }
       float pf[2][4];
-      softmax_frag(cur, g.scale, lane, pf);
+      softmax_frag(cur, sl2, gi, q, pf);
+      const uint32_t uoff = (uint32_t)(2 * lr) * row_pitch + (uint32_t)((2 * lc * g.Cp + hd * HD) * 2);
       // ---- dA[P][Q] = sum_c dy[pix P][c] v[pix Q][c] : A operand = dy rows, B operand ("col") = v rows
       float da[2][4];
 #pragma unroll
       for (int nb = 0; nb < 2; ++nb) da[nb][0] = da[nb][1] = da[nb][2] = da[nb][3] = 0.f;
       {
-        const int mi = lane >> 3, r = lane & 7;
-        // dy rows as A operand: matrix mi -> rows (mi&1)*8 + r, channels (mi>>1)*8 (+16 for the second k-step)
-        const bf16* ga = win_row(sG, zero, g, lr, lc, hd, (mi & 1) * 8 + r);
-        const int gco = (ga == zero) ? 0 : (mi >> 1) * 8;
-        uint32_t a0[4], a1[4];
-        ldsm_x4(a0, smem_u32(ga + gco));
-        ldsm_x4(a1, smem_u32(ga + (ga == zero ? 0 : 16) + gco));
-        // v rows as B operand: for n-block nb, rows Q = nb*8 + r, matrix mi -> channel chunk mi*8
+        uint32_t a0[4], a1[4], bq[4];
+        const uint32_t ga = L.zT ? zero_s : sG_s + uoff + L.offT;
+        ldsm_x4(a0, ga);
+        ldsm_x4(a1, L.zT ? zero_s : ga + 32);
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) {
-          const bf16* vb = win_row(sV, zero, g, lr, lc, hd, nb * 8 + r);
-          uint32_t bq[4];
-          ldsm_x4(bq, smem_u32(vb + (vb == zero ? 0 : mi * 8)));
+          ldsm_x4(bq, L.zB[nb] ? zero_s : sV_s + uoff + L.offB[nb]);
           mma16816(da[nb], a0, bq[0], bq[1]);
           mma16816(da[nb], a1, bq[2], bq[3]);
         }
       }
-      // ---- dlogits = scale * A o (dA - sum_Q A o dA)   (only the own unit's rows: the halo band belongs to the neighbour)
+      // ---- dlogits = scale * A o (dA - sum_Q A o dA)   (own rows only: the halo row belongs to the next band)
       float r0 = pf[0][0] * da[0][0] + pf[0][1] * da[0][1] + pf[1][0] * da[1][0];
       float r1 = pf[0][2] * da[0][2] + pf[0][3] * da[0][3] + pf[1][2] * da[1][2];
       r0 = quad_sum(r0);
       r1 = quad_sum(r1);
       if (lr < g.TR) {
-        bf16* dl = dlogits + lbase;
-        dl[gi * 9 + 2 * q] = __float2bfloat16_rn(g.scale * pf[0][0] * (da[0][0] - r0));
-        dl[gi * 9 + 2 * q + 1] = __float2bfloat16_rn(g.scale * pf[0][1] * (da[0][1] - r0));
-        if (q == 0) dl[gi * 9 + 8] = __float2bfloat16_rn(g.scale * pf[1][0] * (da[1][0] - r0));
+        bf16* dl = dlbase + (size_t)u * g.lpitch + hd * 81;
+        bf16* drow = dl + gi * 9 + 2 * q;
+        drow[0] = __float2bfloat16_rn(g.scale * pf[0][0] * (da[0][0] - r0));
+        drow[1] = __float2bfloat16_rn(g.scale * pf[0][1] * (da[0][1] - r0));
+        if (q == 0) drow[8] = __float2bfloat16_rn(g.scale * pf[1][0] * (da[1][0] - r0));
         if (gi == 0) {
           dl[72 + 2 * q] = __float2bfloat16_rn(g.scale * pf[0][2] * (da[0][2] - r1));
           dl[72 + 2 * q + 1] = __float2bfloat16_rn(g.scale * pf[0][3] * (da[0][3] - r1));
           if (q == 0) dl[80] = __float2bfloat16_rn(g.scale * pf[1][2] * (da[1][2] - r1));
         }
-        if (hd == 0 && lane >= 9 && lane - 9 < g.lpitch - g.heads * 81)
-          dlogits[lbase + g.heads * 81 + (lane - 9)] = __float2bfloat16_rn(0.f);     // zero the TMA padding columns
+        if (hd == 0 && lane >= 9 && lane - 9 < npad)
+          dlbase[(size_t)u * g.lpitch + g.heads * 81 + (lane - 9)] = __float2bfloat16_rn(0.f);   // TMA padding columns
       }
       // ---- dvw[Q][c] = sum_P A[P][Q] dy[pix P][c] : A operand = A^T (movmatrix), B operand = dy rows (ldmatrix.trans)
       const uint32_t at[4] = {movmatrix_t(pack_bf16(pf[0][0], pf[0][1])), movmatrix_t(pack_bf16(pf[1][0], pf[1][1])),
@@ -306,11 +358,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) outlook_bwd_mma_kernel(const bf16
       float acc[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-      mma_rows(acc, at, sG, zero, g, lr, lc, hd, lane);
-      stage_unit(sOut, u, acc, lane);
+      mma_rows(acc, at, sG_s + uoff, zero_s, L);
+      stage_unit(sOut_s + (uint32_t)(u * 9 * OS * 4), acc, L, gi);
+      lc += nwarp;
+      while (lc >= g.w) { lc -= g.w; ++lr; }
     }
     __syncthreads();
-    gather_store(sOut, dv, g, b, i0, hd, nWR);
+    gather_store<NT>(sOut_s, ddst, g, rows, nWR, hd, ly0, lx0);
     __syncthreads();
   }
 }
@@ -319,45 +373,48 @@ int plan(Geo& g, bool bwd, size_t& smem) {
   const int C = g.heads * HD;
   g.Cp = C + 8;
   g.PC = 2 * g.w + 3;
-  // prefer a band small enough for two CTAs per SM (one CTA's staging / stores overlap the other's math)
-  const size_t limits[2] = {(size_t)110 * 1024, (size_t)200 * 1024};
-  for (int pass = 0; pass < 2; ++pass)
-    for (int tr = 4; tr >= 1; --tr) {
-      g.TR = tr;
-      g.nWR = tr + 1;
-      g.PR = 2 * tr + 3;
-      const size_t tile = (size_t)g.PR * g.PC * g.Cp * sizeof(bf16);
-      smem = 64 + tile * (bwd ? 2 : 1) + (size_t)g.nWR * g.w * 9 * OS * sizeof(float);
-      if (smem <= limits[pass]) return 0;
-    }
+  for (int tr = 3; tr >= 1; --tr) {      // largest band that fits: the halo window row is recomputed ((TR+1)/TR work)
+    g.TR = tr;
+    g.nWR = tr + 1;
+    g.PR = 2 * tr + 3;
+    const size_t tile = (size_t)g.PR * g.PC * g.Cp * sizeof(bf16);
+    smem = 64 + tile * (bwd ? 2 : 1) + (size_t)g.nWR * g.w * 9 * OS * sizeof(float);
+    if (smem <= 220 * 1024) return 0;
+  }
   return APB_ERR_UNSUPPORTED;
+}
+
+Geo make_geo(int B, int H, int W, int heads, float scale, int lpitch) {
+  Geo g;
+  g.B = B; g.H = H; g.W = W; g.heads = heads; g.h = (H + 1) / 2; g.w = (W + 1) / 2; g.lpitch = lpitch; g.scale = scale;
+  return g;
 }
 
 }  // namespace
 
 int apb_outlook_fwd_mma(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int lpitch,
                         cudaStream_t st) {
-  Geo g;
-  g.B = B; g.H = H; g.W = W; g.heads = heads; g.h = (H + 1) / 2; g.w = (W + 1) / 2; g.lpitch = lpitch; g.scale = scale;
+  Geo g = make_geo(B, H, W, heads, scale, lpitch);
   size_t smem;
   if (plan(g, false, smem) != 0) return APB_ERR_UNSUPPORTED;
-  cudaFuncSetAttribute(outlook_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  constexpr int NT = 1024;
+  cudaFuncSetAttribute(outlook_fwd_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ceil_div(g.h, g.TR), B);
-  outlook_fwd_mma_kernel<<<grid, NTHREADS, smem, st>>>((const bf16*)v, (const bf16*)logits, (bf16*)y, g);
+  outlook_fwd_mma_kernel<NT><<<grid, NT, smem, st>>>((const bf16*)v, (const bf16*)logits, (bf16*)y, g);
   APB_LAUNCH_CHECK("outlook_fwd_mma");
   return 0;
 }
 
 int apb_outlook_bwd_mma(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
                         int heads, float scale, int lpitch, cudaStream_t st) {
-  Geo g;
-  g.B = B; g.H = H; g.W = W; g.heads = heads; g.h = (H + 1) / 2; g.w = (W + 1) / 2; g.lpitch = lpitch; g.scale = scale;
+  Geo g = make_geo(B, H, W, heads, scale, lpitch);
   size_t smem;
   if (plan(g, true, smem) != 0) return APB_ERR_UNSUPPORTED;
-  cudaFuncSetAttribute(outlook_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  constexpr int NT = 640;
+  cudaFuncSetAttribute(outlook_bwd_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ceil_div(g.h, g.TR), B);
-  outlook_bwd_mma_kernel<<<grid, NTHREADS, smem, st>>>((const bf16*)v, (const bf16*)logits, (const bf16*)dy, (bf16*)dv,
-                                                       (bf16*)dlogits, g);
+  outlook_bwd_mma_kernel<NT><<<grid, NT, smem, st>>>((const bf16*)v, (const bf16*)logits, (const bf16*)dy, (bf16*)dv,
+                                                    (bf16*)dlogits, g);
   APB_LAUNCH_CHECK("outlook_bwd_mma");
   return 0;
 }

@@ -117,3 +117,41 @@ def test_volo_d1_full_size_step_runs_and_is_deterministic():
     assert out[0].shape == (8, 1000) and out[1].shape == (8, 196, 1000)
     assert np.isfinite(res[0][0]) and abs(res[0][0] - 10.36) < 0.5   # ~ (1 + 0.5) * ln(1000) at init
     assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+
+
+@pytest.mark.parametrize('bf16', [False, True])
+def test_deit_against_oracle(bf16):
+    """DeiT (timm ViT restated; parity unpinned upstream): kernels vs oracle.vit_forward on a small config, incl. elastic depth."""
+    from oracle import volo_cpu as O
+    from autoprog_b200.deit import VisionTransformer
+    from functools import partial
+    from autoprog_b200.volo import LayerNorm
+    dev = need_gpu()
+    torch.manual_seed(3)
+    m = VisionTransformer(img_size=64, patch_size=16, num_classes=10, embed_dim=64, depth=4, num_heads=2, mlp_ratio=4,
+                          qkv_bias=True, norm_layer=partial(LayerNorm, eps=1e-6), return_dense=True).to(dev)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.dim() > 1:
+                p.mul_(8.0)
+            elif 'bias' in n:
+                p.normal_(0, 0.1)
+    m.set_sample_config({'layer_num': 3, 'min_layer_num': 2, 'max_layer_num': 4})
+    skip = [i for i, b in enumerate(m.blocks) if getattr(b, 'is_identity_layer', False)]
+    assert len(skip) == 1
+    x = torch.randn(3, 3, 64, 64, device=dev)
+    with A.autocast(enabled=bf16):
+        out, aux = m(x)
+    (out.float().square().sum() + aux.float().square().mean()).backward()
+    sd = {k: v.detach().double().cpu().requires_grad_(True) for k, v in m.state_dict().items()}
+    ro, ra = O.vit_forward(sd, x.double().cpu(), depth=4, heads=2, patch=16, eps=1e-6, skip=skip, dense=True)
+    (ro.square().sum() + ra.square().mean()).backward()
+    t = 2e-2 if bf16 else 1e-5
+    assert rel(out, ro) < t and rel(aux, ra) < t, (rel(out, ro), rel(aux, ra))
+    params = dict(m.named_parameters())
+    flat = torch.cat([params[k].grad.flatten().double().cpu() for k in params if sd[k].grad is not None and params[k].grad is not None])
+    ref = torch.cat([sd[k].grad.flatten() for k in params if sd[k].grad is not None and params[k].grad is not None])
+    assert float((flat - ref).norm() / ref.norm()) < t
+    for k in params:   # identity layer: no gradient
+        if k.startswith(f'blocks.{skip[0]}.'):
+            assert params[k].grad is None or float(params[k].grad.abs().max()) == 0.0
