@@ -309,6 +309,40 @@ def gelu_bwd(x, dy):
     return dx
 
 
+def bn_supported(C: int) -> bool:
+    return C % 8 == 0 and C <= 2048 and 256 % (C // 8) == 0
+
+
+def bn_relu_fwd(x, gamma, beta, running_mean, running_var, momentum: float, eps: float, training: bool):
+    """x [.., C] channels-last flattened.  Returns (y, mean, invstd)."""
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    y = torch.empty_like(x)
+    if training:
+        mean = torch.empty(Cc, device=x.device, dtype=torch.float32)
+        invstd = torch.empty(Cc, device=x.device, dtype=torch.float32)
+    else:
+        mean = running_mean.detach().float().contiguous()
+        invstd = torch.rsqrt(running_var.detach().float() + eps).contiguous()
+    ws = torch.empty(int(lib().apb_bn_workspace_floats(rows, Cc)), device=x.device, dtype=torch.float32)
+    check(lib().apb_bn_relu_fwd(_p(x), _p(y), _p(gamma), _p(beta), _p(mean), _p(invstd), _p(running_mean) if training else None,
+                                _p(running_var) if training else None, momentum, eps, int(training), _p(ws), rows, Cc, dt(x),
+                                _st()), 'bn_relu_fwd')
+    return y, mean, invstd
+
+
+def bn_relu_bwd(x, y, dy, gamma, mean, invstd):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    dx = torch.empty_like(x)
+    dg = torch.empty(Cc, device=x.device, dtype=torch.float32)
+    db = torch.empty(Cc, device=x.device, dtype=torch.float32)
+    ws = torch.empty(int(lib().apb_bn_workspace_floats(rows, Cc)), device=x.device, dtype=torch.float32)
+    check(lib().apb_bn_relu_bwd(_p(x), _p(y), _p(dy), _p(gamma), _p(mean), _p(invstd), _p(dx), _p(dg), _p(db), _p(ws), rows, Cc,
+                                dt(x), _st()), 'bn_relu_bwd')
+    return dx, dg, db
+
+
 def adamw_ema(p, g, m, v, hyper, beta1, beta2, eps, wd, emas=(), decays=(), shadow=None):
     """hyper: device fp32 tensor [lr, 1-beta1^t, sqrt(1-beta2^t)]."""
     n = p.numel()

@@ -326,6 +326,28 @@ class CastFn(torch.autograd.Function):
         return K.cast(_c(dy), ctx.src), None
 
 
+class BNReLUFn(torch.autograd.Function):
+    """BatchNorm2d (train: batch statistics + running-stat update; eval: running stats) + ReLU on an NHWC tensor
+    (PatchEmbed stem, models/volo.py:358-368)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, momentum, eps, training):
+        xc = _c(x)
+        y, mean, invstd = K.bn_relu_fwd(xc, weight.detach().float(), bias.detach().float(), running_mean, running_var,
+                                        momentum, eps, training)
+        ctx.save_for_backward(xc, y, weight.detach().float(), mean, invstd)
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, y, w, mean, invstd = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError('BNReLUFn: backward through eval-mode BatchNorm is not supported')
+        dx, dg, db = K.bn_relu_bwd(xc, y, K.cast(_c(dy), xc.dtype), w, mean, invstd)
+        return dx, dg, db, None, None, None, None, None
+
+
 class ResidualAddFn(torch.autograd.Function):
     """out = x + rs[b] * r : x fp32 stream, r compute dtype (DropPath scale rs optional, not differentiated)."""
 

@@ -323,14 +323,39 @@ class PatchEmbed(nn.Module):
                               stride=patch_size // stem_stride)
         self.num_patches = (img_size // patch_size) ** 2
 
+    def _stem(self, x):
+        """conv (cuDNN) -> fused BatchNorm+ReLU kernel, three times; NCHW logical / channels-last physical."""
+        mods = list(self.conv)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            fuse = (isinstance(m, nn.Conv2d) and i + 2 < len(mods) and isinstance(mods[i + 1], nn.BatchNorm2d)
+                    and isinstance(mods[i + 2], nn.ReLU) and K.bn_supported(mods[i + 1].num_features)
+                    and mods[i + 1].affine and mods[i + 1].track_running_stats and mods[i + 1].momentum is not None)
+            if not fuse:
+                x = m(x)
+                i += 1
+                continue
+            bn = mods[i + 1]
+            x = m(x)
+            use_batch = bn.training
+            if use_batch:
+                with torch.no_grad():
+                    bn.num_batches_tracked += 1
+            y = ops.BNReLUFn.apply(x.permute(0, 2, 3, 1), bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                   float(bn.momentum), float(bn.eps), use_batch)
+            x = y.permute(0, 3, 1, 2)
+            i += 3
+        return x
+
     def forward_nhwc(self, x):
         if self.stem_conv:
             x = x.contiguous(memory_format=torch.channels_last)
             if torch.is_autocast_enabled('cuda'):
-                x = self.conv(x)
+                x = self._stem(x)
             else:   # fp32 parity mode: keep cuDNN off TF32
                 with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                    x = self.conv(x)
+                    x = self._stem(x)
         x = x.permute(0, 2, 3, 1)   # free for channels_last
         return ops.PatchConvFn.apply(x, self.proj.weight, self.proj.bias, self.proj.kernel_size[0])
 

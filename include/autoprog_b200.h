@@ -137,6 +137,20 @@ int apb_add(const void* a, const void* b, void* out, long long n, int dtype, apb
 int apb_gelu_fwd(const void* x, void* y, long long n, int dtype, apb_stream_t stream);
 int apb_gelu_bwd(const void* x, const void* dy, void* dx, long long n, int dtype, apb_stream_t stream);
 
+/* ---- train-mode BatchNorm2d + ReLU on channels-last activations (PatchEmbed stem, models/volo.py:355-368)
+ * x,y,dy,dx [rows, C] NHWC-flattened (dtype); gamma,beta,mean,invstd,running_* fp32 [C]; C % 8 == 0.
+ * fwd: use_batch_stats=1 computes batch mean / invstd (saved for backward) and updates the running statistics like
+ * nn.BatchNorm2d (momentum, unbiased running variance); use_batch_stats=0 applies the given mean/invstd (eval).
+ * bwd: g = dy * (y > 0); dbeta = sum g; dgamma = sum g*xhat; dx = gamma*invstd*(g - dbeta/rows - xhat*dgamma/rows).
+ * workspace: apb_bn_workspace_floats(rows, C) floats. */
+long long apb_bn_workspace_floats(long long rows, int C);
+int apb_bn_relu_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean, float* invstd,
+                    float* running_mean, float* running_var, float momentum, float eps, int use_batch_stats,
+                    float* workspace, long long rows, int C, int dtype, apb_stream_t stream);
+int apb_bn_relu_bwd(const void* x, const void* y, const void* dy, const float* gamma, const float* mean,
+                    const float* invstd, void* dx, float* dgamma, float* dbeta, float* workspace, long long rows, int C,
+                    int dtype, apb_stream_t stream);
+
 /* ---- fused AdamW + k EMA updates + bf16 shadow weights in one pass over the parameters
  * (timm create_optimizer('adamw') + 4 x ModelEmaV2.update, main_prog.py:1019-1033)
  * p,g,m,v fp32 [n]; ema: array (device) of n_ema fp32 pointers, decay: host array of n_ema floats (<= 8);

@@ -385,3 +385,33 @@ def test_gemm_binding_wgrad_split_k_deterministic():
     assert torch.equal(dw1, dw2)
     ref = dy.double().t() @ x.double()
     assert rel(dw1, ref) < 1e-5
+
+
+@pytest.mark.parametrize('dtype', DT)
+@pytest.mark.parametrize('rows,C', [(4 * 32 * 32, 64), (3 * 17 * 13, 8), (2 * 20 * 20, 128)])
+def test_batchnorm_relu_fused(rows, C, dtype):
+    """fused train-mode BatchNorm2d + ReLU (stem) vs torch in fp64, incl. running-stat update and eval mode."""
+    dev = need_gpu()
+    torch.manual_seed(rows + C)
+    x = q(torch.randn(rows, C) * 1.5 + 0.3, dtype)
+    dy = q(torch.randn(rows, C), dtype)
+    g, b = (1 + 0.3 * torch.randn(C)).float(), (0.2 * torch.randn(C)).float()
+    rm, rv = torch.randn(C).float() * 0.1, (1 + 0.2 * torch.rand(C)).float()
+    bn = torch.nn.BatchNorm1d(C, momentum=0.1, eps=1e-5).double()
+    with torch.no_grad():
+        bn.weight.copy_(g); bn.bias.copy_(b); bn.running_mean.copy_(rm); bn.running_var.copy_(rv)
+    xr = x.clone().requires_grad_(True)
+    yr = torch.relu(bn(xr))
+    yr.backward(dy)
+    rmd, rvd = rm.clone().to(dev), rv.clone().to(dev)
+    y, mean, invstd = K.bn_relu_fwd(x.to(dev, dtype), g.to(dev), b.to(dev), rmd, rvd, 0.1, 1e-5, True)
+    t = tol(dtype)
+    assert rel(y, yr) < t
+    assert rel(rmd, bn.running_mean) < 1e-5 and rel(rvd, bn.running_var) < 1e-5
+    # backward uses the mask of the STORED output, so feed the oracle's mask through the same rounding
+    dx, dg, db = K.bn_relu_bwd(x.to(dev, dtype), y, dy.to(dev, dtype), g.to(dev), mean, invstd)
+    assert rel(dx, xr.grad) < (t if dtype == torch.float32 else 3e-2), rel(dx, xr.grad)
+    assert rel(dg, bn.weight.grad) < max(t, 1e-4) and rel(db, bn.bias.grad) < max(t, 1e-4)
+    bn.eval()
+    ye, _, _ = K.bn_relu_fwd(x.to(dev, dtype), g.to(dev), b.to(dev), rmd, rvd, 0.1, 1e-5, False)
+    assert rel(ye, torch.relu(bn(x))) < t
