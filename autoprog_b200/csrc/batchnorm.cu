@@ -80,14 +80,18 @@ __global__ void __launch_bounds__(256) bn_colstats_kernel(const T* __restrict__ 
   }
 }
 
-// finalize forward statistics: mean, invstd; update running stats.  One thread per channel.
-__global__ void bn_finalize_fwd_kernel(const float* __restrict__ part, int nparts, int C, long long rows, float eps,
-                                       float momentum, float* __restrict__ mean, float* __restrict__ invstd,
-                                       float* __restrict__ running_mean, float* __restrict__ running_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// finalize forward statistics: mean, invstd; update running stats.  One warp per channel (fixed-order tree).
+__global__ void __launch_bounds__(256) bn_finalize_fwd_kernel(const float* __restrict__ part, int nparts, int C, long long rows,
+                                                              float eps, float momentum, float* __restrict__ mean,
+                                                              float* __restrict__ invstd, float* __restrict__ running_mean,
+                                                              float* __restrict__ running_var) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double s = 0.0, ss = 0.0;
-  for (int p = 0; p < nparts; ++p) { s += (double)part[(size_t)p * 2 * C + c]; ss += (double)part[(size_t)p * 2 * C + C + c]; }
+  for (int p = lane; p < nparts; p += 32) { s += (double)part[(size_t)p * 2 * C + c]; ss += (double)part[(size_t)p * 2 * C + C + c]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+  if (lane != 0) return;
   const double m = s / (double)rows;
   double var = ss / (double)rows - m * m;
   if (var < 0.0) var = 0.0;
@@ -100,15 +104,16 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ part, int npart
   }
 }
 
-// finalize backward sums: dbeta = sum g, dgamma = sum g*xhat (fixed order)
-__global__ void bn_finalize_bwd_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// finalize backward sums: dbeta = sum g, dgamma = sum g*xhat (one warp per channel, fixed order)
+__global__ void __launch_bounds__(256) bn_finalize_bwd_kernel(const float* __restrict__ part, int nparts, int C,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   float s = 0.f, ss = 0.f;
-  for (int p = 0; p < nparts; ++p) { s += part[(size_t)p * 2 * C + c]; ss += part[(size_t)p * 2 * C + C + c]; }
-  dbeta[c] = s;
-  dgamma[c] = ss;
+  for (int p = lane; p < nparts; p += 32) { s += part[(size_t)p * 2 * C + c]; ss += part[(size_t)p * 2 * C + C + c]; }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if (lane == 0) { dbeta[c] = s; dgamma[c] = ss; }
 }
 
 // y = relu((x - mean) * invstd * gamma + beta)
@@ -189,7 +194,7 @@ int apb_bn_relu_fwd(const void* x, void* y, const float* gamma, const float* bet
       bn_colstats_kernel<bf16, 0><<<parts, 256, smem, st>>>((const bf16*)x, nullptr, nullptr, nullptr, nullptr, rows, C, workspace, BN_ROWS_PER_CTA);
     }
     APB_LAUNCH_CHECK("bn_colstats");
-    bn_finalize_fwd_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, parts, C, rows, eps, momentum, mean, invstd, running_mean, running_var);
+    bn_finalize_fwd_kernel<<<ceil_div(C, 8), 256, 0, st>>>(workspace, parts, C, rows, eps, momentum, mean, invstd, running_mean, running_var);
     APB_LAUNCH_CHECK("bn_finalize_fwd");
   }
   const long long nvec = rows * (C / 8);
@@ -213,13 +218,13 @@ int apb_bn_relu_bwd(const void* x, const void* y, const void* dy, const float* g
     cudaFuncSetAttribute(bn_colstats_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     bn_colstats_kernel<float, 1><<<parts, 256, smem, st>>>((const float*)x, (const float*)y, (const float*)dy, mean, invstd, rows, C, workspace, BN_ROWS_PER_CTA);
     APB_LAUNCH_CHECK("bn_colstats_bwd");
-    bn_finalize_bwd_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, parts, C, dgamma, dbeta);
+    bn_finalize_bwd_kernel<<<ceil_div(C, 8), 256, 0, st>>>(workspace, parts, C, dgamma, dbeta);
     bn_bwd_apply_kernel<float><<<bn_grid(nvec), 256, 0, st>>>((const float*)x, (const float*)y, (const float*)dy, mean, invstd, gamma, dgamma, dbeta, (float*)dx, rows, C);
   } else {
     cudaFuncSetAttribute(bn_colstats_kernel<bf16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     bn_colstats_kernel<bf16, 1><<<parts, 256, smem, st>>>((const bf16*)x, (const bf16*)y, (const bf16*)dy, mean, invstd, rows, C, workspace, BN_ROWS_PER_CTA);
     APB_LAUNCH_CHECK("bn_colstats_bwd");
-    bn_finalize_bwd_kernel<<<ceil_div(C, 128), 128, 0, st>>>(workspace, parts, C, dgamma, dbeta);
+    bn_finalize_bwd_kernel<<<ceil_div(C, 8), 256, 0, st>>>(workspace, parts, C, dgamma, dbeta);
     bn_bwd_apply_kernel<bf16><<<bn_grid(nvec), 256, 0, st>>>((const bf16*)x, (const bf16*)y, (const bf16*)dy, mean, invstd, gamma, dgamma, dbeta, (bf16*)dx, rows, C);
   }
   APB_LAUNCH_CHECK("bn_bwd_apply");

@@ -35,37 +35,54 @@ __global__ void avgpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, 
   }
 }
 
-template <typename T>
+// one thread = VEC contiguous channels (16 bytes)
+template <typename T, int VEC>
 __global__ void avgpool2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int H, int W, int C, int h, int w,
                                     int accumulate) {
-  const long long n = (long long)B * H * W * C;
+  const int cv = C / VEC;
+  const long long n = (long long)B * H * W * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % C);
-    long long r = idx / C;
+    const int c = (int)(idx % cv) * VEC;
+    long long r = idx / cv;
     const int xx = (int)(r % W); r /= W;
     const int yy = (int)(r % H);
     const int b = (int)(r / H);
     const int i = yy >> 1, j = xx >> 1;
-    const int cnt = ((2 * i + 1 < H) ? 2 : 1) * ((2 * j + 1 < W) ? 2 : 1);
-    float g = to_f(dy[(((size_t)b * h + i) * w + j) * C + c]) / (float)cnt;
-    if (accumulate) g += to_f(dx[idx]);
-    dx[idx] = from_f<T>(g);
+    const float inv = 1.f / (float)(((2 * i + 1 < H) ? 2 : 1) * ((2 * j + 1 < W) ? 2 : 1));
+    const T* src = dy + (((size_t)b * h + i) * w + j) * C + c;
+    T* dst = dx + (size_t)(idx / cv) * C + c;
+    if (VEC * sizeof(T) == 16) {
+      Vec16<T> g, o;
+      g.load(src);
+      if (accumulate) o.load(dst);
+#pragma unroll
+      for (int k = 0; k < Vec16<T>::N; ++k) o.set(k, g.get(k) * inv + (accumulate ? o.get(k) : 0.f));
+      o.store(dst);
+    } else {
+      float g = to_f(*src) * inv;
+      if (accumulate) g += to_f(*dst);
+      *dst = from_f<T>(g);
+    }
   }
 }
 
 // ---- mix-token / un-mix (models/volo.py:655-658, 687-689)
-template <typename T>
+template <typename T, int VEC>
 __global__ void flip_in_box_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int r0, int c0,
                                    int r1, int c1) {
-  const long long n = (long long)B * H * W * C;
+  const int cv = C / VEC;
+  const long long n = (long long)B * H * W * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-    long long r = idx / C;
+    const int c = (int)(idx % cv) * VEC;
+    long long r = idx / cv;
     const int xx = (int)(r % W); r /= W;
     const int yy = (int)(r % H);
     const int b = (int)(r / H);
     const bool inside = (yy >= r0 && yy < r1 && xx >= c0 && xx < c1);
-    const long long src = inside ? idx + (long long)(B - 1 - 2 * b) * H * W * C : idx;
-    y[idx] = x[src];
+    const size_t pix = (size_t)(idx / cv);
+    const size_t spix = inside ? pix + (size_t)((long long)(B - 1 - 2 * b) * H * W) : pix;
+    if (VEC * sizeof(T) == 16) *reinterpret_cast<uint4*>(y + pix * C + c) = *reinterpret_cast<const uint4*>(x + spix * C + c);
+    else y[pix * C + c] = x[spix * C + c];
   }
 }
 
@@ -253,9 +270,20 @@ int apb_avgpool2_bwd(const void* dy, void* dx, int B, int H, int W, int C, int a
   const int h = (H + 1) / 2, w = (W + 1) / 2;
   const long long n = (long long)B * H * W * C;
   if (n <= 0) return 0;
+  const bool al = (((uintptr_t)dy | (uintptr_t)dx) & 15) == 0;
+  if (dtype == APB_F32 && C % 4 == 0 && al) {
+    avgpool2_bwd_kernel<float, 4><<<ew_grid(n / 4), EW_THREADS, 0, st>>>((const float*)dy, (float*)dx, B, H, W, C, h, w, accumulate);
+    APB_LAUNCH_CHECK("avgpool2_bwd");
+    return 0;
+  }
+  if (dtype == APB_BF16 && C % 8 == 0 && al) {
+    avgpool2_bwd_kernel<bf16, 8><<<ew_grid(n / 8), EW_THREADS, 0, st>>>((const bf16*)dy, (bf16*)dx, B, H, W, C, h, w, accumulate);
+    APB_LAUNCH_CHECK("avgpool2_bwd");
+    return 0;
+  }
   DISPATCH_T(dtype, "avgpool2_bwd",
-             (avgpool2_bwd_kernel<float><<<ew_grid(n), EW_THREADS, 0, st>>>((const float*)dy, (float*)dx, B, H, W, C, h, w, accumulate)),
-             (avgpool2_bwd_kernel<bf16><<<ew_grid(n), EW_THREADS, 0, st>>>((const bf16*)dy, (bf16*)dx, B, H, W, C, h, w, accumulate)));
+             (avgpool2_bwd_kernel<float, 1><<<ew_grid(n), EW_THREADS, 0, st>>>((const float*)dy, (float*)dx, B, H, W, C, h, w, accumulate)),
+             (avgpool2_bwd_kernel<bf16, 1><<<ew_grid(n), EW_THREADS, 0, st>>>((const bf16*)dy, (bf16*)dx, B, H, W, C, h, w, accumulate)));
   return 0;
 }
 
@@ -265,9 +293,20 @@ int apb_flip_in_box(const void* x, void* y, int B, int H, int W, int C, int r0, 
   APB_CHECK_ARG(x != y, APB_ERR_ARG, "flip_in_box: must be out of place");
   const long long n = (long long)B * H * W * C;
   if (n <= 0) return 0;
+  const bool al = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  if (dtype == APB_F32 && C % 4 == 0 && al) {
+    flip_in_box_kernel<float, 4><<<ew_grid(n / 4), EW_THREADS, 0, st>>>((const float*)x, (float*)y, B, H, W, C, r0, c0, r1, c1);
+    APB_LAUNCH_CHECK("flip_in_box");
+    return 0;
+  }
+  if (dtype == APB_BF16 && C % 8 == 0 && al) {
+    flip_in_box_kernel<bf16, 8><<<ew_grid(n / 8), EW_THREADS, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C, r0, c0, r1, c1);
+    APB_LAUNCH_CHECK("flip_in_box");
+    return 0;
+  }
   DISPATCH_T(dtype, "flip_in_box",
-             (flip_in_box_kernel<float><<<ew_grid(n), EW_THREADS, 0, st>>>((const float*)x, (float*)y, B, H, W, C, r0, c0, r1, c1)),
-             (flip_in_box_kernel<bf16><<<ew_grid(n), EW_THREADS, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C, r0, c0, r1, c1)));
+             (flip_in_box_kernel<float, 1><<<ew_grid(n), EW_THREADS, 0, st>>>((const float*)x, (float*)y, B, H, W, C, r0, c0, r1, c1)),
+             (flip_in_box_kernel<bf16, 1><<<ew_grid(n), EW_THREADS, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C, r0, c0, r1, c1)));
   return 0;
 }
 

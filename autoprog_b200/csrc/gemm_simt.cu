@@ -70,11 +70,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TI* __restrict__ A
       const size_t o = (size_t)m * N + n;
       float v = acc[i][j] + (bias != nullptr ? bias[n] : 0.f);
       if (epilogue == 1) {
-        const TO pre = from_f<TO>(v);
-        aux[o] = pre;
-        C[o] = from_f<TO>(gelu_f(to_f(pre)));
+        aux[o] = from_f<TO>(dgelu_f(v));          // gelu'(pre-activation): all the backward epilogue needs
+        C[o] = from_f<TO>(gelu_f(v));
       } else if (epilogue == 2) {
-        C[o] = from_f<TO>(v * dgelu_f(to_f(aux[o])));
+        C[o] = from_f<TO>(v * to_f(aux[o]));
       } else if (epilogue == 3) {
         C[o] = from_f<TO>(to_f(C[o]) + v);
       } else {

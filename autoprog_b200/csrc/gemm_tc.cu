@@ -24,8 +24,6 @@
 namespace {
 
 constexpr int BM = 128, BK = 64;
-constexpr int EPI_WARPS = 16;
-constexpr int NTHREADS = 64 + EPI_WARPS * 32;
 constexpr int ACC_STAGES = 2;
 
 struct TcParams {
@@ -144,18 +142,18 @@ __device__ __forceinline__ uint8_t* stg64(uint8_t* stg, int row, int chunk) {
   return stg + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a,
+template <int BN, int STAGES, int EPI_WARPS>
+__global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                              const __grid_constant__ CUtensorMap tma_b,
                                                              const __grid_constant__ CUtensorMap tma_c,
                                                              const __grid_constant__ CUtensorMap tma_x, TcParams p) {
   constexpr uint32_t A_BYTES = BM * BK * 2;   // 16 KB
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;
+  constexpr uint32_t TMEM_COLS = (ACC_STAGES * BN <= 256) ? 256 : 512;   // power of two >= 2 accumulator stages
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr uint32_t STG_BYTES = 4096 + 2048;   // per epilogue warp: a 32 x 128 B box (C) + a 32 x 64 B box (aux)
+  constexpr uint32_t STG_BYTES = 4096 + ((BN / 32) / (EPI_WARPS / 4)) * 2048;   // per epilogue warp: 4 KB of C boxes + one 2 KB aux box per chunk
   uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + EPI_WARPS * STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -249,32 +247,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
+    constexpr int NCH = (BN / 32) / (EPI_WARPS / 4);   // 32-column chunks per warp
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may touch
-    const int cg = (warp - 2) >> 2;               // which 32-column slice of the tile
-    uint8_t* stg0 = stg_base + (warp - 2) * STG_BYTES;   // C box   (bf16: 32 x 64 B, fp32: 32 x 128 B)
-    uint8_t* stg1 = stg0 + 4096;                         // aux box (bf16 32 x 64 B)
+    const int cg = (warp - 2) >> 2;               // which column slice of the tile
+    uint8_t* stgC = stg_base + (warp - 2) * STG_BYTES;   // bf16: NCH boxes of 32 x 64 B; fp32: one 32 x 128 B box
+    uint8_t* stgX = stgC + 4096;                         // aux boxes (bf16 32 x 64 B each)
     uint32_t ai = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ai) {
       const int z = item % p.splits, t = item / p.splits;
       const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
       const uint32_t as = ai % ACC_STAGES;
-      const int cb = n0 + cg * 32;                // first column of this warp's sub-tile
-      const int rb = m0 + quarter * 32;           // first row
-      if (p.epilogue == 2 && cb < p.N && rb < p.M) {
-        // dGELU: fetch the pre-activation sub-tile (coalesced, 4 lanes per 64-byte row) while the MMAs of this tile run
+      const int rb = m0 + quarter * 32;           // first row of this warp's sub-tile
+      const int cb0 = n0 + cg * NCH * 32;         // first column
+      if (p.epilogue == 2 && rb < p.M) {
+        // dGELU: fetch the gelu'(pre-activation) sub-tiles (coalesced, 4 lanes per 64-byte row) while this tile's MMAs run
         const bf16* ax = reinterpret_cast<const bf16*>(p.aux);
 #pragma unroll
-        for (int itr = 0; itr < 4; ++itr) {
-          const int rr = itr * 8 + (lane >> 2), ch = lane & 3;
-          uint4 val = make_uint4(0u, 0u, 0u, 0u);
-          if (rb + rr < p.M && cb + ch * 8 < p.N) val = *reinterpret_cast<const uint4*>(ax + (size_t)(rb + rr) * p.N + cb + ch * 8);
-          *reinterpret_cast<uint4*>(stg64(stg1, rr, ch)) = val;
+        for (int c = 0; c < NCH; ++c) {
+          const int cb = cb0 + c * 32;
+          if (cb >= p.N) continue;
+#pragma unroll
+          for (int itr = 0; itr < 4; ++itr) {
+            const int rr = itr * 8 + (lane >> 2), ch = lane & 3;
+            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+            if (rb + rr < p.M && cb + ch * 8 < p.N) val = *reinterpret_cast<const uint4*>(ax + (size_t)(rb + rr) * p.N + cb + ch * 8);
+            *reinterpret_cast<uint4*>(stg64(stgX + c * 2048, rr, ch)) = val;
+          }
         }
       }
       mbar_wait(&tfull_bar[as], (ai / ACC_STAGES) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)(cg * 32), r);
+      uint32_t r[NCH][32];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)((cg * NCH + c) * 32), r[c]);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -283,68 +289,80 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const __grid_const
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous TMA stores have drained the staging boxes
       }
       __syncwarp();
-      if (cb >= p.N || rb >= p.M) continue;
-      float v[32];
+      if (rb >= p.M) continue;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      if (p.bias != nullptr) {
+      for (int c = 0; c < NCH; ++c) {
+        const int cb = cb0 + c * 32;
+        if (cb >= p.N) continue;
+        uint8_t* sx = stgX + c * 2048;
+        float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          if (cb + j < p.N) {                     // N % 8 == 0 on this path
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + j));
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c][j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (cb + j < p.N) {                     // N % 8 == 0 on this path
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+        }
+        if (p.epilogue == 2) {
+          __syncwarp();                             // prefetched gelu' sub-tile is complete
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const uint4 pk = *reinterpret_cast<const uint4*>(stg64(sx, lane, ch));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int tt = 0; tt < 4; ++tt) {
+              v[ch * 8 + 2 * tt] *= __bfloat162float(h2[tt].x);
+              v[ch * 8 + 2 * tt + 1] *= __bfloat162float(h2[tt].y);
+            }
           }
-      }
-      if (p.epilogue == 2) {
-        // dGELU: the pre-activation sub-tile was prefetched into stg1 above; read the own row back
+        } else if (p.epilogue == 1) {
+          // GELU: C = gelu(v); aux = gelu'(v) (what the dgrad epilogue multiplies by); Phi and the Gaussian are shared
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint4 pk;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int tt = 0; tt < 4; ++tt) {
+              float c0, e0, c1, e1;
+              const float x0 = v[ch * 8 + 2 * tt], x1 = v[ch * 8 + 2 * tt + 1];
+              phi_fast(x0, c0, e0);
+              phi_fast(x1, c1, e1);
+              h2[tt] = __floats2bfloat162_rn(fmaf(x0 * 0.39894228040143267794f, e0, c0), fmaf(x1 * 0.39894228040143267794f, e1, c1));
+              v[ch * 8 + 2 * tt] = x0 * c0;
+              v[ch * 8 + 2 * tt + 1] = x1 * c1;
+            }
+            *reinterpret_cast<uint4*>(stg64(sx, lane, ch)) = pk;
+          }
+        }
+        uint8_t* sc = p.out_f32 ? stgC : stgC + c * 2048;
+        if (p.out_f32) {
+          if (c > 0) {                              // the single fp32 box is reused: wait until the previous store has read it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+          }
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch)
+            *reinterpret_cast<float4*>(stg128(sc, lane, ch)) = make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint4 pk;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int tt = 0; tt < 4; ++tt) h2[tt] = __floats2bfloat162_rn(v[ch * 8 + 2 * tt], v[ch * 8 + 2 * tt + 1]);
+            *reinterpret_cast<uint4*>(stg64(sc, lane, ch)) = pk;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const uint4 pk = *reinterpret_cast<const uint4*>(stg64(stg1, lane, ch));
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&pk);
-#pragma unroll
-          for (int tt = 0; tt < 4; ++tt) {
-            v[ch * 8 + 2 * tt] *= dgelu_f(__bfloat162float(h2[tt].x));
-            v[ch * 8 + 2 * tt + 1] *= dgelu_f(__bfloat162float(h2[tt].y));
-          }
+        if (lane == 0) {
+          tma_store_3d(&tma_c, sc, cb, rb, z);
+          if (p.epilogue == 1) tma_store_3d(&tma_x, sx, cb, rb, 0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        __syncwarp();
-      } else if (p.epilogue == 1) {
-        // GELU: store the rounded pre-activation (what backward re-reads) and activate that rounded value
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint4 pk;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-          for (int tt = 0; tt < 4; ++tt) h2[tt] = __floats2bfloat162_rn(v[ch * 8 + 2 * tt], v[ch * 8 + 2 * tt + 1]);
-          *reinterpret_cast<uint4*>(stg64(stg1, lane, ch)) = pk;
-#pragma unroll
-          for (int tt = 0; tt < 4; ++tt) {
-            v[ch * 8 + 2 * tt] = gelu_f(__bfloat162float(h2[tt].x));
-            v[ch * 8 + 2 * tt + 1] = gelu_f(__bfloat162float(h2[tt].y));
-          }
-        }
-      }
-      if (p.out_f32) {
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          *reinterpret_cast<float4*>(stg128(stg0, lane, ch)) = make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
-      } else {
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint4 pk;
-          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-          for (int tt = 0; tt < 4; ++tt) h2[tt] = __floats2bfloat162_rn(v[ch * 8 + 2 * tt], v[ch * 8 + 2 * tt + 1]);
-          *reinterpret_cast<uint4*>(stg64(stg0, lane, ch)) = pk;
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_3d(&tma_c, stg0, cb, rb, z);
-        if (p.epilogue == 1) tma_store_3d(&tma_x, stg1, cb, rb, 0);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -425,13 +443,13 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int EPI_WARPS>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mx, TcParams p, int splits,
            cudaStream_t st) {
-  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + EPI_WARPS * (4096 + 2048) + 1024 + 256;
+  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + EPI_WARPS * (4096 + ((BN / 32) / (EPI_WARPS / 4)) * 2048) + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { apb_set_error("gemm_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
@@ -440,7 +458,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
   p.splits = splits;
   const long long items = (long long)p.tiles_m * p.tiles_n * splits;
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  gemm_tc_kernel<BN, STAGES><<<grid, NTHREADS, smem, st>>>(ma, mb, mc, mx, p);
+  gemm_tc_kernel<BN, STAGES, EPI_WARPS><<<grid, 64 + EPI_WARPS * 32, smem, st>>>(ma, mb, mc, mx, p);
   APB_LAUNCH_CHECK("gemm_tc");
   return 0;
 }
@@ -473,7 +491,9 @@ int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* 
   int rc;
   if (!trans_a) rc = make_map(&ma, A, M, K, BM, BK); else rc = make_map(&ma, A, K, M, BK, 64);
   if (rc) return rc;
-  const int BN = 128;
+  // tile width: 192 when it wastes no more columns than 128 (N = 192, 384, 576, 768, 1152, ...): 20 % less L2 operand
+  // traffic per FLOP and fewer tiles; otherwise 128
+  const int BN = (ceil_div(N, 192) * 192 <= ceil_div(N, 128) * 128) ? 192 : 128;
   if (!trans_b) rc = make_map(&mb, B, N, K, BN, BK); else rc = make_map(&mb, B, K, N, BK, 64);
   if (rc) return rc;
   TcParams p;
@@ -490,12 +510,14 @@ int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* 
   if (rc) return rc;
   rc = make_map_out(&mx, (epilogue == 1) ? aux : C, (epilogue == 1) ? false : (p.out_f32 != 0), M, N, (epilogue == 1) ? 1 : splits);
   if (rc) return rc;
-  return launch<128, 4>(ma, mb, mc, mx, p, splits, st);
+  if (BN == 192) return launch<192, 3, 12>(ma, mb, mc, mx, p, splits, st);
+  return launch<128, 4, 16>(ma, mb, mc, mx, p, splits, st);
 }
 
 // number of K splits the wgrad-shaped GEMM should use to fill the GPU (host helper for the binding)
 int apb_gemm_tc_suggest_split(int M, int N, int K) {
-  const int tiles = ceil_div(M, BM) * ceil_div(N, 128);
+  const int bn = (ceil_div(N, 192) * 192 <= ceil_div(N, 128) * 128) ? 192 : 128;
+  const int tiles = ceil_div(M, BM) * ceil_div(N, bn);
   const int total_kb = (K + BK - 1) / BK;
   const int sms = 148;
   if (tiles >= sms || total_kb < 16) return 1;

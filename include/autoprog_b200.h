@@ -74,8 +74,8 @@ int apb_colsum(const void* a, long long rows, int C, float* out, int accumulate,
  * 161-167,188,199,253-254,370-373,389; fwd = NT, dgrad = NN, wgrad = TN via the transpose flags)
  *   trans_a = 0: A stored [M,K] row-major; 1: A stored [K,M] row-major.
  *   trans_b = 0: B stored [N,K] row-major (nn.Linear weight); 1: B stored [K,N] row-major.
- *   epilogue: 0 none | 1 GELU: aux = acc+bias (pre-activation, out dtype), C = gelu(aux)
- *             | 2 dGELU: C = acc * gelu'(aux)  | 3 accumulate: C += acc (out fp32 only)
+ *   epilogue: 0 none | 1 GELU: u = acc+bias, C = gelu(u), aux = gelu'(u) (out dtype; saved for the backward)
+ *             | 2 dGELU: C = acc * aux  | 3 accumulate: C += acc (SIMT only)
  *   in_dtype: dtype of A and B; out_dtype: dtype of C/aux; bias fp32 or NULL.
  * apb_gemm_simt: CUDA-core fp32-accumulate path (exact fp32 products; parity mode, any shape).
  * apb_gemm_tc  : tcgen05/TMEM/TMA bf16 path (in_dtype must be APB_BF16; K % 8 == 0 etc.). */

@@ -185,13 +185,13 @@ def test_gemm_simt(M, N, Kd, ta, tb, dtype):
     aux = torch.empty_like(out)
     K.check(lib.apb_gemm_simt(A_.data_ptr(), B_.data_ptr(), out.data_ptr(), bias.float().to(dev).data_ptr(), aux.data_ptr(), M, N,
                               Kd, int(ta), int(tb), 1, K.dt(A_), K.dt(out), torch.cuda.current_stream().cuda_stream), 'gemm')
-    assert rel(aux, ref) < (2e-6 if dtype == torch.float32 else 5e-3)
-    assert rel(out, O.gelu(aux.double().cpu())) < (2e-6 if dtype == torch.float32 else 5e-3)
+    u = ref.clone().requires_grad_(True)
+    O.gelu(u).backward(torch.ones_like(u))          # u.grad = gelu'(pre-activation)
+    assert rel(aux, u.grad) < (2e-6 if dtype == torch.float32 else 5e-3)
+    assert rel(out, O.gelu(ref)) < (2e-6 if dtype == torch.float32 else 5e-3)
     K.check(lib.apb_gemm_simt(A_.data_ptr(), B_.data_ptr(), out.data_ptr(), None, aux.data_ptr(), M, N, Kd, int(ta), int(tb), 2,
                               K.dt(A_), K.dt(out), torch.cuda.current_stream().cuda_stream), 'gemm')
-    u = aux.double().cpu().requires_grad_(True)
-    O.gelu(u).backward(a @ b.t())
-    assert rel(out, u.grad) < (3e-6 if dtype == torch.float32 else 6e-3)
+    assert rel(out, (a @ b.t()) * aux.double().cpu()) < (3e-6 if dtype == torch.float32 else 6e-3)
 
 
 @pytest.mark.parametrize('dtype', DT)
@@ -355,12 +355,12 @@ def test_gemm_tc_vs_fp64(M, N, Kd, ta, tb):
     aux = torch.zeros_like(out)
     K.check(lib.apb_gemm_tc(A_.data_ptr(), B_.data_ptr(), out.data_ptr(), bias.to(dev).data_ptr(), aux.data_ptr(), M, N, Kd, int(ta),
                             int(tb), 1, K.BF16, K.BF16, 1, st), 'gemm_tc')
-    assert rel(aux, ref + bias.double()) < 4e-3 and rel(out, O.gelu(aux.double().cpu())) < 4e-3
+    u = (ref + bias.double()).clone().requires_grad_(True)
+    O.gelu(u).backward(torch.ones_like(u))          # u.grad = gelu'(pre-activation)
+    assert rel(aux, u.grad) < 4e-3 and rel(out, O.gelu(ref + bias.double())) < 4e-3
     K.check(lib.apb_gemm_tc(A_.data_ptr(), B_.data_ptr(), out.data_ptr(), None, aux.data_ptr(), M, N, Kd, int(ta), int(tb), 2,
                             K.BF16, K.BF16, 1, st), 'gemm_tc')
-    u = aux.double().cpu().requires_grad_(True)
-    O.gelu(u).backward(ref)
-    assert rel(out, u.grad) < 5e-3
+    assert rel(out, ref * aux.double().cpu()) < 5e-3
     # split-K partials + fixed-order reduction (the wgrad path) through the binding
     if Kd >= 192:
         for split in (2, 3):
