@@ -36,6 +36,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float ex2(float x) {   // bare MUFU.EX2 (inputs are <= 0 here; denormal results flush to 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -88,7 +93,7 @@ __device__ __forceinline__ void mma_rows(float (&o)[4][4], const uint32_t (&pa)[
   }
 }
 
-__global__ void __launch_bounds__(256) mhsa_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+__global__ void __launch_bounds__(256, 3) mhsa_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                            float* __restrict__ lse, int N, int heads, float scale,
                                                            int rows_pad) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(256) mhsa_fwd_mma_kernel(const bf16* __restric
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const float mn = fmaxf(m_run[h], quad_max(mt[h]));
-        corr[h] = exp2f((m_run[h] - mn) * sl2);
+        corr[h] = ex2((m_run[h] - mn) * sl2);
         m_run[h] = mn;
         l_run[h] *= corr[h];
       }
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(256) mhsa_fwd_mma_kernel(const bf16* __restric
       for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float pv = exp2f((s[nb][j] - m_run[j >> 1]) * sl2);
+          const float pv = ex2((s[nb][j] - m_run[j >> 1]) * sl2);
           s[nb][j] = pv;
           l_run[j >> 1] += pv;
         }
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(256) mhsa_rowdot_kernel(const bf16* __restrict
 }
 
 // dQ: warp per 16 queries; S = Q K^T, P = exp(S*scale - lse), dP = dO V^T, dS = P*(dP - D), dQ = scale * dS K
-__global__ void __launch_bounds__(256) mhsa_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+__global__ void __launch_bounds__(256, 3) mhsa_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                               const float* __restrict__ lse, const float* __restrict__ drow,
                                                               bf16* __restrict__ dqkv, int N, int heads, float scale,
                                                               int rows_pad) {
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(256) mhsa_bwd_dq_mma_kernel(const bf16* __rest
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int key = k0 + nb * 8 + 2 * q + (j & 1);
-          const float pv = (key < N) ? exp2f(s[nb][j] * sl2 - l2[j >> 1]) : 0.f;
+          const float pv = (key < N) ? ex2(s[nb][j] * sl2 - l2[j >> 1]) : 0.f;
           s[nb][j] = pv * (dp[nb][j] - dr[j >> 1]);
         }
       }
@@ -313,7 +318,7 @@ __global__ void __launch_bounds__(256) mhsa_bwd_dkv_mma_kernel(const bf16* __res
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int qi = i0 + nb * 8 + 2 * q + (j & 1);
-          const float pv = (qi < N) ? exp2f(s[nb][j] * sl2 - sL[qi]) : 0.f;
+          const float pv = (qi < N) ? ex2(s[nb][j] * sl2 - sL[qi]) : 0.f;
           s[nb][j] = pv;
           dp[nb][j] = pv * (dp[nb][j] - sD[qi]);
         }
