@@ -149,7 +149,32 @@ __global__ void __launch_bounds__(256) colsum_v8_kernel(const T* __restrict__ a,
   }
 }
 
+// out[i] = sum_s parts[s][i] (fixed order): the deterministic tail of the split-K wgrad GEMM, one launch
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ parts, float* __restrict__ out, int splits,
+                                                            long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = reinterpret_cast<const float4*>(parts)[i];
+    for (int s = 1; s < splits; ++s) {
+      const float4 v = reinterpret_cast<const float4*>(parts)[(long long)s * n4 + i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+}
+
 }  // namespace
+
+int apb_splitk_reduce(const float* parts, float* out, int splits, long long n, apb_stream_t stream) {
+  cudaStream_t st = APB_STREAM(stream);
+  APB_CHECK_ARG(splits >= 1 && n > 0 && (n % 4) == 0 && (((uintptr_t)parts | (uintptr_t)out) & 15) == 0, APB_ERR_ARG,
+                "splitk_reduce: splits=%d n=%lld (n must be a multiple of 4, pointers 16-byte aligned)", splits, n);
+  const long long n4 = n / 4;
+  long long grid = (n4 + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  splitk_reduce_kernel<<<(int)grid, 256, 0, st>>>(parts, out, splits, n4);
+  APB_LAUNCH_CHECK("splitk_reduce");
+  return 0;
+}
 
 // returns 1 if handled, 0 if the caller must use the scalar kernel, <0 / >1 on error
 int ln_bwd_v4_launch(const void* dy, const void* xs, const float* mean, const float* rstd, const float* gamma,

@@ -51,6 +51,10 @@ class FlatGroup:
                 self.flat_p[o:o + p.numel()].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[o:o + p.numel()].view(p.shape)
                 p.grad = self.flat_g[o:o + p.numel()].view(p.shape)
+                # destination for kernels that write a parameter gradient in place (ops.grad_dest): when `.grad` is
+                # None at backward time the wgrad GEMM / reductions write straight into the flat buffer and autograd
+                # adopts that view -- no per-parameter accumulate kernel
+                p._apb_grad_view = p.grad
         if self.shadow is not None:
             self.shadow.copy_(self.flat_p)
 
@@ -68,7 +72,10 @@ class FlatGroup:
                 p.grad = view
 
     def zero_grad(self):
+        """Zero the flat buffer and detach the `.grad` views: backward re-attaches them (direct writes, see above)."""
         self.flat_g.zero_()
+        for p in self.params:
+            p.grad = None
 
 
 class FlatState:

@@ -99,27 +99,34 @@ def ln_fwd(x, gamma, beta, eps: float, out_dtype, r=None, rs=None, rows_per_samp
     return xs, y, mean, rstd
 
 
-def ln_bwd(dy, xs, mean, rstd, gamma, dres=None, want_dr: bool = False, rs=None, rows_per_sample: int = 1):
-    """Returns (dxs, dr, dgamma, dbeta); dxs = dres + LN'(dy) (stream dtype of xs); dr = rs[b]*dxs in dy's dtype."""
+def ln_bwd(dy, xs, mean, rstd, gamma, dres=None, want_dr: bool = False, rs=None, rows_per_sample: int = 1, dg_out=None,
+           db_out=None):
+    """Returns (dxs, dr, dgamma, dbeta); dxs = dres + LN'(dy) (stream dtype of xs); dr = rs[b]*dxs in dy's dtype.
+    dg_out / db_out: optional fp32 destinations (views of the flat gradient buffer) written in place."""
     Cc = xs.shape[-1]
     rows = xs.numel() // Cc
     dxs = torch.empty_like(xs)
-    dg = torch.empty(Cc, device=xs.device, dtype=torch.float32)
-    db = torch.empty(Cc, device=xs.device, dtype=torch.float32)
+    dg = dg_out if dg_out is not None else torch.empty(Cc, device=xs.device, dtype=torch.float32)
+    db = db_out if db_out is not None else torch.empty(Cc, device=xs.device, dtype=torch.float32)
     ws = torch.empty(int(lib().apb_ln_bwd_workspace_floats(Cc)), device=xs.device, dtype=torch.float32)
     if dres is not None:
         assert dres.dtype == xs.dtype and dres.shape == xs.shape
     dr = torch.empty(xs.shape, device=xs.device, dtype=dy.dtype) if want_dr else None
     check(lib().apb_ln_bwd(_p(dy), _p(xs), _p(mean), _p(rstd), _p(gamma), _p(dres), _p(dxs), _p(dr), _p(rs), rows_per_sample,
                            _p(dg), _p(db), 0, _p(ws), rows, Cc, dt(xs), dt(dy), _st()), 'ln_bwd')
+    if dg_out is not None:
+        dg = dg.detach()           # fresh aliases so autograd can adopt them as `.grad` without cloning
+    if db_out is not None:
+        db = db.detach()
     return dxs, dr, dg, db
 
 
-def colsum(a: torch.Tensor, Cc: Optional[int] = None) -> torch.Tensor:
+def colsum(a: torch.Tensor, Cc: Optional[int] = None, out=None) -> torch.Tensor:
     """fp32 column sums of a viewed as [rows, C] (bias gradients, batch reductions)."""
     Cc = Cc or a.shape[-1]
     rows = a.numel() // Cc
-    out = torch.empty(Cc, device=a.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(Cc, device=a.device, dtype=torch.float32)
     ws = torch.empty(max(1, int(lib().apb_colsum_workspace_floats(rows, Cc))), device=a.device, dtype=torch.float32)
     check(lib().apb_colsum(_p(a), rows, Cc, _p(out), 0, _p(ws), dt(a), _st()), 'colsum')
     return out
@@ -152,8 +159,7 @@ def gemm(a, b, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = Fa
         parts = torch.empty((split, M, N), device=a.device, dtype=torch.float32)
         check(lib().apb_gemm_tc(_p(a), _p(b), _p(parts), None, None, M, N, K, int(trans_a), int(trans_b), 0, dt(a), F32,
                                 split, _st()), 'gemm_tc(split-k)')
-        ws = torch.empty(M * N, device=a.device, dtype=torch.float32)
-        check(lib().apb_colsum(_p(parts), split, M * N, _p(out), 0, _p(ws), F32, _st()), 'gemm_tc(split-k reduce)')
+        check(lib().apb_splitk_reduce(_p(parts), _p(out), split, M * N, _st()), 'gemm_tc(split-k reduce)')
         return out
     check(lib().apb_gemm_tc(_p(a), _p(b), _p(out), _p(bias), _p(aux), M, N, K, int(trans_a), int(trans_b), epilogue, dt(a),
                             _CODES[out_dtype], 1, _st()), 'gemm_tc')

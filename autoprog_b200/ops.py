@@ -86,8 +86,16 @@ def _lin_fwd(x2d, w, bias, epilogue=K.EPI_NONE):
     return K.gemm(x2d, w, M, w.shape[0], Kd, bias=bias, epilogue=epilogue)
 
 
-def _lin_bwd(dy2d, x2d, w, need_dx=True, need_dw=True, need_db=True, dgelu_aux=None):
-    """Returns (dx [M,K] compute dtype, dw [N,K] fp32, db [N] fp32)."""
+def grad_dest(p):
+    """Flat-gradient view a kernel may write this parameter's gradient into (see flat.FlatGroup): only when the
+    parameter has no `.grad` yet -- i.e. not while gradients are being accumulated over several backward passes."""
+    if p is None or p.grad is not None:
+        return None
+    return getattr(p, '_apb_grad_view', None)
+
+
+def _lin_bwd(dy2d, x2d, w, need_dx=True, need_dw=True, need_db=True, dgelu_aux=None, dw_out=None, db_out=None):
+    """Returns (dx [M,K] compute dtype, dw [N,K] fp32, db [N] fp32).  dw_out / db_out: in-place destinations."""
     M, N = dy2d.shape
     Kd = w.shape[1]
     dx = dw = db = None
@@ -97,9 +105,17 @@ def _lin_bwd(dy2d, x2d, w, need_dx=True, need_dw=True, need_db=True, dgelu_aux=N
         else:
             dx = K.gemm(dy2d, w, M, Kd, N, trans_b=True)
     if need_dw:
-        dw = K.gemm(dy2d, x2d, N, Kd, M, trans_a=True, trans_b=True, out_dtype=F32)
+        if dw_out is not None and tuple(dw_out.shape) != (N, Kd):
+            dw_out = None
+        dw = K.gemm(dy2d, x2d, N, Kd, M, trans_a=True, trans_b=True, out_dtype=F32, out=dw_out)
+        if dw_out is not None:
+            dw = dw.detach()       # fresh alias: autograd adopts it as `.grad` without cloning (sole reference)
     if need_db:
-        db = K.colsum(dy2d, N)
+        if db_out is not None and db_out.numel() != N:
+            db_out = None
+        db = K.colsum(dy2d, N, out=db_out)
+        if db_out is not None:
+            db = db.detach()
     return dx, dw, db
 
 
@@ -119,6 +135,7 @@ class LinearFn(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.x_dtype = x.dtype
         ctx.x_shape = x.shape
+        ctx.params = (weight, bias)
         return y.reshape(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
@@ -126,7 +143,8 @@ class LinearFn(torch.autograd.Function):
         xc, w = ctx.saved_tensors
         dy2 = _c(K.cast(_c(dy), xc.dtype)).reshape(-1, w.shape[0])
         dx, dw, db = _lin_bwd(dy2, xc, w, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                              ctx.has_bias and ctx.needs_input_grad[2])
+                              ctx.has_bias and ctx.needs_input_grad[2], dw_out=grad_dest(ctx.params[0]),
+                              db_out=grad_dest(ctx.params[1]))
         if dx is not None:
             dx = K.cast(dx, ctx.x_dtype).reshape(ctx.x_shape)
         return dx, dw, db
@@ -399,9 +417,9 @@ class _BlockBase(torch.autograd.Function):
         return u, hdn, z
 
     @staticmethod
-    def _mlp_bwd(dz, n2, u, hdn, w1, w2):
-        du, dw2, db2 = _lin_bwd(dz, hdn, w2, dgelu_aux=u)
-        dn2, dw1, db1 = _lin_bwd(du, n2, w1)
+    def _mlp_bwd(dz, n2, u, hdn, w1, w2, P):
+        du, dw2, db2 = _lin_bwd(dz, hdn, w2, dgelu_aux=u, dw_out=grad_dest(P['w2']), db_out=grad_dest(P['b2']))
+        dn2, dw1, db1 = _lin_bwd(du, n2, w1, dw_out=grad_dest(P['w1']), db_out=grad_dest(P['b1']))
         return dn2, dw1, db1, dw2, db2
 
 
@@ -456,6 +474,7 @@ class OutlookerFn(_BlockBase):
                               n1w.detach(), n2w.detach(), rs_in if rs_in is not None else x.new_empty(0),
                               rs_blk if rs_blk is not None else x.new_empty(0))
         ctx.meta = (heads, scale, r_in is not None, rs_in is not None, rs_blk is not None, nl)
+        ctx.P = dict(n1w=n1w, n1b=n1b, wv=wv, wp=wp, bp=bp, n2w=n2w, n2b=n2b, w1=w1, b1=b1, w2=w2, b2=b2)
         return x1, z.reshape(B, H, W, Cc)
 
     @staticmethod
@@ -466,19 +485,22 @@ class OutlookerFn(_BlockBase):
         B, H, W, Cc = xs.shape
         rps = H * W
         cdt = n1.dtype
+        P = ctx.P
         dz2 = _flat(K.cast(_c(dz), cdt))
-        dn2, dw1, db1, dw2, db2 = _BlockBase._mlp_bwd(dz2, _flat(n2), u, hdn, c1, c2)
+        dn2, dw1, db1, dw2, db2 = _BlockBase._mlp_bwd(dz2, _flat(n2), u, hdn, c1, c2, P)
         dx1, do, dn2w, dn2b = K.ln_bwd(dn2.reshape(xs.shape), x1, mu2, rstd2, n2w, dres=_c(dx1_out), want_dr=True,
-                                       rs=rs_blk if has_rs_blk else None, rows_per_sample=rps)
+                                       rs=rs_blk if has_rs_blk else None, rows_per_sample=rps,
+                                       dg_out=grad_dest(P['n2w']), db_out=grad_dest(P['n2b']))
         do2 = _flat(do)
-        dy, dwp, dbp = _lin_bwd(do2, _flat(y), cp)
+        dy, dwp, dbp = _lin_bwd(do2, _flat(y), cp, dw_out=grad_dest(P['wp']), db_out=grad_dest(P['bp']))
         dv, dlg = K.outlook_bwd(v, lg, dy.reshape(xs.shape), heads, scale)
-        dn1, dwv, _ = _lin_bwd(_flat(dv), _flat(n1), cv, need_db=False)
+        dn1, dwv, _ = _lin_bwd(_flat(dv), _flat(n1), cv, need_db=False, dw_out=grad_dest(P['wv']))
         dpooled, dwa, dba = _lin_bwd(_flat(dlg), _flat(pooled), ca)
         dwa, dba = dwa[:nl], dba[:nl]                      # drop the padding rows
         dn1 = K.avgpool2_bwd(dpooled.reshape(pooled.shape), H, W, accumulate_into=dn1.reshape(xs.shape))
         dxs, dr, dn1w, dn1b = K.ln_bwd(dn1, xs, mu1, rstd1, n1w, dres=dx1, want_dr=has_r,
-                                       rs=rs_in if has_rs_in else None, rows_per_sample=rps)
+                                       rs=rs_in if has_rs_in else None, rows_per_sample=rps,
+                                       dg_out=grad_dest(P['n1w']), db_out=grad_dest(P['n1b']))
         return (dxs, dr, None, None, None, None, dn1w, dn1b, dwv, dwa, dba, dwp, dbp, dn2w, dn2b, dw1, db1, dw2, db2)
 
 
@@ -506,6 +528,7 @@ class TransformerFn(_BlockBase):
                               n1w.detach(), n2w.detach(), rs_in if rs_in is not None else x.new_empty(0),
                               rs_blk if rs_blk is not None else x.new_empty(0))
         ctx.meta = (heads, scale, r_in is not None, rs_in is not None, rs_blk is not None, bqkv is not None, N)
+        ctx.P = dict(n1w=n1w, n1b=n1b, wqkv=wqkv, bqkv=bqkv, wp=wp, bp=bp, n2w=n2w, n2b=n2b, w1=w1, b1=b1, w2=w2, b2=b2)
         return x1, z.reshape(shp)
 
     @staticmethod
@@ -514,13 +537,17 @@ class TransformerFn(_BlockBase):
          rs_blk) = ctx.saved_tensors
         heads, scale, has_r, has_rs_in, has_rs_blk, has_bqkv, N = ctx.meta
         cdt = n1.dtype
+        P = ctx.P
         dz2 = _flat(K.cast(_c(dz), cdt))
-        dn2, dw1, db1, dw2, db2 = _BlockBase._mlp_bwd(dz2, _flat(n2), u, hdn, c1, c2)
+        dn2, dw1, db1, dw2, db2 = _BlockBase._mlp_bwd(dz2, _flat(n2), u, hdn, c1, c2, P)
         dx1, do, dn2w, dn2b = K.ln_bwd(dn2.reshape(xs.shape), x1, mu2, rstd2, n2w, dres=_c(dx1_out), want_dr=True,
-                                       rs=rs_blk if has_rs_blk else None, rows_per_sample=N)
-        da, dwp, dbp = _lin_bwd(_flat(do), _flat(a), cp)
+                                       rs=rs_blk if has_rs_blk else None, rows_per_sample=N,
+                                       dg_out=grad_dest(P['n2w']), db_out=grad_dest(P['n2b']))
+        da, dwp, dbp = _lin_bwd(_flat(do), _flat(a), cp, dw_out=grad_dest(P['wp']), db_out=grad_dest(P['bp']))
         dqkv = K.mhsa_bwd(qkv, a, da.reshape(a.shape), lse, heads, scale)
-        dn1, dwqkv, dbqkv = _lin_bwd(_flat(dqkv), _flat(n1), cqkv, need_db=has_bqkv)
+        dn1, dwqkv, dbqkv = _lin_bwd(_flat(dqkv), _flat(n1), cqkv, need_db=has_bqkv, dw_out=grad_dest(P['wqkv']),
+                                     db_out=grad_dest(P['bqkv']))
         dxs, dr, dn1w, dn1b = K.ln_bwd(dn1.reshape(xs.shape), xs, mu1, rstd1, n1w, dres=dx1, want_dr=has_r,
-                                       rs=rs_in if has_rs_in else None, rows_per_sample=N)
+                                       rs=rs_in if has_rs_in else None, rows_per_sample=N,
+                                       dg_out=grad_dest(P['n1w']), db_out=grad_dest(P['n1b']))
         return (dxs, dr, None, None, None, None, dn1w, dn1b, dwqkv, dbqkv, dwp, dbp, dn2w, dn2b, dw1, db1, dw2, db2)

@@ -86,6 +86,8 @@ int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* 
 /* split_k > 1 (wgrad: few output tiles, very long K): C receives split_k fp32 partial products [split_k][M][N] that
  * the caller sums in fixed order (apb_colsum over the split dim) -> deterministic; bias/epilogue must be 0/NULL. */
 int apb_gemm_tc_suggest_split(int M, int N, int K);
+/* out[i] = sum_s parts[s][i] in fixed order (n % 4 == 0): the reduction of the split-K partials. */
+int apb_splitk_reduce(const float* parts, float* out, int splits, long long n, apb_stream_t stream);
 
 /* ---- multi-head self-attention core  softmax(q k^T * scale) v  (models/volo.py:188-197)
  * qkv [B,N,3*heads*D] laid out (3, heads, D) per token; out [B,N,heads*D]; lse [B,heads,N] fp32 (saved for bwd).

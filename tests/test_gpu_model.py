@@ -155,3 +155,40 @@ def test_deit_against_oracle(bf16):
     for k in params:   # identity layer: no gradient
         if k.startswith(f'blocks.{skip[0]}.'):
             assert params[k].grad is None or float(params[k].grad.abs().max()) == 0.0
+
+
+def test_flat_direct_gradient_writes_match_autograd_accumulation():
+    """FusedAdamW's flat storage: gradients written in place by the kernels == gradients accumulated by autograd,
+    and a second backward without zero_grad accumulates (batch-splits path, prog/scaler.py update=False)."""
+    from autoprog_b200.optim import FusedAdamW
+    dev = need_gpu()
+    torch.manual_seed(0)
+    m = A.create_model('model_variant', variant='volo_h2_l4', img_size=64, num_classes=16).to(dev)
+    x = torch.randn(4, 3, 64, 64, device=dev)
+    tgt = torch.softmax(torch.randn(4, 16, 18, device=dev), 1)
+    crit = A.TokenLabelCrossEntropy(dense_weight=0.5)
+
+    def run():
+        np.random.seed(3)
+        with A.autocast():
+            loss = crit(m(x), tgt)
+        loss.backward()
+    m.zero_grad(set_to_none=True)
+    run()
+    ref = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    opt = FusedAdamW(m, lr=1e-3, weight_decay=0.05)
+    opt.zero_grad()
+    assert all(p.grad is None for p in m.parameters())
+    run()
+    flat_ptrs = {id(p): v.data_ptr() for g in opt.flat.groups for p, v in zip(g.params, g.views(g.flat_g))}
+    n_direct = 0
+    for n, p in m.named_parameters():
+        assert torch.equal(p.grad, ref[n]), n
+        n_direct += int(p.grad.data_ptr() == flat_ptrs[id(p)])
+    assert n_direct >= 0.8 * len(ref), n_direct          # almost every gradient landed in the flat buffer directly
+    opt.flat.ensure_grad_views()
+    for n, p in m.named_parameters():
+        assert p.grad.data_ptr() == flat_ptrs[id(p)] and torch.equal(p.grad, ref[n]), n
+    run()                                                # no zero_grad: accumulate
+    for n, p in m.named_parameters():
+        assert rel(p.grad, 2 * ref[n]) < 1e-6, n
