@@ -21,7 +21,7 @@ SIGNATURES = {
     'apb_outlook_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     'apb_outlook_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     'apb_tlce_workspace_floats': (_ll, [_i, _i]),
-    'apb_tlce_fwd_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
+    'apb_tlce_fwd_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
     'apb_scale_by_scalar': (_i, [_vp, _vp, _ll, _vp, _i, _vp]),
     'apb_ln_fwd': (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _f, _i, _i, _vp]),
     'apb_ln_bwd_workspace_floats': (_ll, [_i]),
@@ -41,6 +41,7 @@ SIGNATURES = {
     'apb_avgpool2_fwd': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'apb_avgpool2_bwd': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'apb_flip_in_box': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    'apb_flip_in_box_dev': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     'apb_patchify': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'apb_unpatchify': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'apb_bicubic_resize': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),

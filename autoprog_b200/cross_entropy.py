@@ -60,7 +60,7 @@ class TokenLabelCrossEntropy(nn.Module):
         if target.dtype != torch.float32:
             target = target.float()
         return ops.TokenLabelCEFn.apply(output, aux_output, target, _area(bb), float(self.cls_weight),
-                                        float(self.dense_weight))
+                                        float(self.dense_weight), getattr(bb, 'dev', None))
 
 
 class TokenLabelGTCrossEntropy(TokenLabelCrossEntropy):

@@ -73,24 +73,33 @@ __device__ __forceinline__ void load_a_rows(uint32_t (&a)[2][4], const bf16* g, 
     }
 }
 
-// S[16 x 8] (+)= A[16 x 32] . M[key0..key0+7][0..31]^T  with M rows in smem (B operand "col": contiguous channel pairs)
-__device__ __forceinline__ void mma_rowsT(float (&c)[4], const uint32_t (&a)[2][4], const bf16* sM, int key0, int lane) {
+// Per-lane ldmatrix byte offsets inside a [rows][ROWP] bf16 tile (loop invariant; all smem addressing is 32-bit):
+//   offT : "rows^T" pattern -- 8 rows x 4 channel chunks (B operand "col" of S = A . M^T)
+//   offR : "rows" pattern   -- 16 rows x 2 channel chunks, used with ldmatrix.trans (B operand of O = P . M)
+__device__ __forceinline__ uint32_t lane_offT(int lane) { return (uint32_t)(((lane & 7) * ROWP + (lane >> 3) * 8) * 2); }
+__device__ __forceinline__ uint32_t lane_offR(int lane) {
+  const int mi = lane >> 3, r = lane & 7;
+  return (uint32_t)((((mi & 1) * 8 + r) * ROWP + (mi >> 1) * 8) * 2);
+}
+constexpr uint32_t ROWB = ROWP * 2;   // row pitch in bytes
+
+// S[16 x 8] (+)= A[16 x 32] . M[key0..key0+7][0..31]^T ; addr = tile + key0*ROWB + lane_offT
+__device__ __forceinline__ void mma_rowsT(float (&c)[4], const uint32_t (&a)[2][4], uint32_t addr) {
   uint32_t b[4];
-  ldsm_x4(b, smem_u32(sM + (key0 + (lane & 7)) * ROWP + (lane >> 3) * 8));
+  ldsm_x4(b, addr);
   mma16816(c, a[0], b[0], b[1]);
   mma16816(c, a[1], b[2], b[3]);
 }
 
-// O[16 x 32] += P[16 x 16 (keys key0..+15)] . M[key0..key0+15][0..31]  (B operand via ldmatrix.trans)
-__device__ __forceinline__ void mma_rows(float (&o)[4][4], const uint32_t (&pa)[4], const bf16* sM, int key0, int lane) {
+// O[16 x 32] += P[16 x 16 (keys key0..+15)] . M[key0..key0+15][0..31] ; addr = tile + key0*ROWB + lane_offR
+__device__ __forceinline__ void mma_rows(float (&o)[4][4], const uint32_t (&pa)[4], uint32_t addr) {
   uint32_t b[4];
-  const int mi = lane >> 3, r = lane & 7;
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    ldsm_x4_t(b, smem_u32(sM + (key0 + (mi & 1) * 8 + r) * ROWP + half * 16 + (mi >> 1) * 8));
-    mma16816(o[half * 2 + 0], pa, b[0], b[1]);
-    mma16816(o[half * 2 + 1], pa, b[2], b[3]);
-  }
+  ldsm_x4_t(b, addr);
+  mma16816(o[0], pa, b[0], b[1]);
+  mma16816(o[1], pa, b[2], b[3]);
+  ldsm_x4_t(b, addr + 32);
+  mma16816(o[2], pa, b[0], b[1]);
+  mma16816(o[3], pa, b[2], b[3]);
 }
 
 __global__ void __launch_bounds__(256, 3) mhsa_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
@@ -108,6 +117,8 @@ __global__ void __launch_bounds__(256, 3) mhsa_fwd_mma_kernel(const bf16* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int gi = lane >> 2, q = lane & 3;
   const float sl2 = scale * 1.4426950408889634f;
+  const uint32_t sK_T = smem_u32(sK) + lane_offT(lane), sV_R = smem_u32(sV) + lane_offR(lane);
+  const int nfull = N / 64;                 // key blocks that need no masking
   for (int row0 = warp * 16; row0 < N; row0 += nwarp * 16) {
     uint32_t qa[2][4];
     load_a_rows(qa, qb, tok, row0, N, lane);
@@ -117,28 +128,34 @@ __global__ void __launch_bounds__(256, 3) mhsa_fwd_mma_kernel(const bf16* __rest
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-    for (int k0 = 0; k0 < N; k0 += 64) {
+    for (int kb = 0; kb * 64 < N; ++kb) {
+      const int k0 = kb * 64;
+      const bool tail = kb >= nfull;        // warp-uniform
       float s[8][4];
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
         s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
-        if (k0 + nb * 8 < N) mma_rowsT(s[nb], qa, sK, k0 + nb * 8, lane);
+        if (!tail || k0 + nb * 8 < N) mma_rowsT(s[nb], qa, sK_T + (uint32_t)(k0 + nb * 8) * ROWB);
+      }
+      if (tail) {
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (k0 + nb * 8 + 2 * q + (j & 1) >= N) s[nb][j] = -INFINITY;
       }
       float mt[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int key = k0 + nb * 8 + 2 * q + (j & 1);
-          if (key >= N) s[nb][j] = -INFINITY;
-          mt[j >> 1] = fmaxf(mt[j >> 1], s[nb][j]);
-        }
-      float corr[2];
+        for (int j = 0; j < 4; ++j) mt[j >> 1] = fmaxf(mt[j >> 1], s[nb][j]);
+      float corr[2], msc[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const float mn = fmaxf(m_run[h], quad_max(mt[h]));
         corr[h] = ex2((m_run[h] - mn) * sl2);
         m_run[h] = mn;
+        msc[h] = mn * sl2;
         l_run[h] *= corr[h];
       }
 #pragma unroll
@@ -147,16 +164,16 @@ __global__ void __launch_bounds__(256, 3) mhsa_fwd_mma_kernel(const bf16* __rest
       for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float pv = ex2((s[nb][j] - m_run[j >> 1]) * sl2);
+          const float pv = ex2(fmaf(s[nb][j], sl2, -msc[j >> 1]));
           s[nb][j] = pv;
           l_run[j >> 1] += pv;
         }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        if (k0 + kk * 16 < N) {
-          uint32_t pa[4] = {pack_bf16(s[2 * kk][0], s[2 * kk][1]), pack_bf16(s[2 * kk][2], s[2 * kk][3]),
-                            pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3])};
-          mma_rows(o, pa, sV, k0 + kk * 16, lane);
+        if (!tail || k0 + kk * 16 < N) {
+          const uint32_t pa[4] = {pack_bf16(s[2 * kk][0], s[2 * kk][1]), pack_bf16(s[2 * kk][2], s[2 * kk][3]),
+                                  pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3])};
+          mma_rows(o, pa, sV_R + (uint32_t)(k0 + kk * 16) * ROWB);
         }
       }
     }
@@ -224,6 +241,7 @@ __global__ void __launch_bounds__(256, 3) mhsa_bwd_dq_mma_kernel(const bf16* __r
   const float sl2 = scale * 1.4426950408889634f;
   const float* L = lse + ((size_t)b * heads + hd) * N;
   const float* Dr = drow + ((size_t)b * heads + hd) * N;
+  const uint32_t sK_T = smem_u32(sK) + lane_offT(lane), sV_T = smem_u32(sV) + lane_offT(lane), sK_R = smem_u32(sK) + lane_offR(lane);
   for (int row0 = warp * 16; row0 < N; row0 += nwarp * 16) {
     uint32_t qa[2][4], ga[2][4];
     load_a_rows(qa, qb, tok, row0, N, lane);
@@ -246,8 +264,8 @@ __global__ void __launch_bounds__(256, 3) mhsa_bwd_dq_mma_kernel(const bf16* __r
       for (int nb = 0; nb < 2; ++nb) {
         s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
         dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
-        mma_rowsT(s[nb], qa, sK, k0 + nb * 8, lane);
-        mma_rowsT(dp[nb], ga, sV, k0 + nb * 8, lane);
+        mma_rowsT(s[nb], qa, sK_T + (uint32_t)(k0 + nb * 8) * ROWB);
+        mma_rowsT(dp[nb], ga, sV_T + (uint32_t)(k0 + nb * 8) * ROWB);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int key = k0 + nb * 8 + 2 * q + (j & 1);
@@ -257,7 +275,7 @@ __global__ void __launch_bounds__(256, 3) mhsa_bwd_dq_mma_kernel(const bf16* __r
       }
       uint32_t pa[4] = {pack_bf16(s[0][0], s[0][1]), pack_bf16(s[0][2], s[0][3]), pack_bf16(s[1][0], s[1][1]),
                         pack_bf16(s[1][2], s[1][3])};
-      mma_rows(dq, pa, sK, k0, lane);
+      mma_rows(dq, pa, sK_R + (uint32_t)k0 * ROWB);
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -297,6 +315,8 @@ __global__ void __launch_bounds__(256) mhsa_bwd_dkv_mma_kernel(const bf16* __res
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int gi = lane >> 2, q = lane & 3;
   const float sl2 = scale * 1.4426950408889634f;
+  const uint32_t sQ_T = smem_u32(sQ) + lane_offT(lane), sG_T = smem_u32(sG) + lane_offT(lane);
+  const uint32_t sQ_R = smem_u32(sQ) + lane_offR(lane), sG_R = smem_u32(sG) + lane_offR(lane);
   for (int key0 = warp * 16; key0 < N; key0 += nwarp * 16) {
     uint32_t ka[2][4], va[2][4];
     load_a_rows(ka, qb + heads * D, tok, key0, N, lane);
@@ -313,8 +333,8 @@ __global__ void __launch_bounds__(256) mhsa_bwd_dkv_mma_kernel(const bf16* __res
       for (int nb = 0; nb < 2; ++nb) {
         s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
         dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
-        mma_rowsT(s[nb], ka, sQ, i0 + nb * 8, lane);     // S^T[key][query]
-        mma_rowsT(dp[nb], va, sG, i0 + nb * 8, lane);    // dP^T[key][query]
+        mma_rowsT(s[nb], ka, sQ_T + (uint32_t)(i0 + nb * 8) * ROWB);     // S^T[key][query]
+        mma_rowsT(dp[nb], va, sG_T + (uint32_t)(i0 + nb * 8) * ROWB);    // dP^T[key][query]
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int qi = i0 + nb * 8 + 2 * q + (j & 1);
@@ -327,8 +347,8 @@ __global__ void __launch_bounds__(256) mhsa_bwd_dkv_mma_kernel(const bf16* __res
         ds[nb * 2 + 0] = pack_bf16(dp[nb][0], dp[nb][1]);
         ds[nb * 2 + 1] = pack_bf16(dp[nb][2], dp[nb][3]);
       }
-      mma_rows(dv, pp, sG, i0, lane);
-      mma_rows(dk, ds, sQ, i0, lane);
+      mma_rows(dv, pp, sG_R + (uint32_t)i0 * ROWB);
+      mma_rows(dk, ds, sQ_R + (uint32_t)i0 * ROWB);
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {

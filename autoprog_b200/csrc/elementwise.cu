@@ -69,7 +69,10 @@ __global__ void avgpool2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx
 // ---- mix-token / un-mix (models/volo.py:655-658, 687-689)
 template <typename T, int VEC>
 __global__ void flip_in_box_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int r0, int c0,
-                                   int r1, int c1) {
+                                   int r1, int c1, const int* __restrict__ box_dev, int box_scale) {
+  if (box_dev != nullptr) {   // CUDA-graph path: the box lives in device memory and changes between replays
+    r0 = box_dev[0] * box_scale; c0 = box_dev[1] * box_scale; r1 = box_dev[2] * box_scale; c1 = box_dev[3] * box_scale;
+  }
   const int cv = C / VEC;
   const long long n = (long long)B * H * W * cv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
@@ -287,26 +290,39 @@ int apb_avgpool2_bwd(const void* dy, void* dx, int B, int H, int W, int C, int a
   return 0;
 }
 
+static int flip_impl(const void* x, void* y, int B, int H, int W, int C, int r0, int c0, int r1, int c1, const int* box_dev,
+                     int box_scale, int dtype, cudaStream_t st);
+
 int apb_flip_in_box(const void* x, void* y, int B, int H, int W, int C, int r0, int c0, int r1, int c1, int dtype,
                     apb_stream_t stream) {
-  cudaStream_t st = APB_STREAM(stream);
+  return flip_impl(x, y, B, H, W, C, r0, c0, r1, c1, nullptr, 1, dtype, APB_STREAM(stream));
+}
+
+int apb_flip_in_box_dev(const void* x, void* y, int B, int H, int W, int C, const int* box_dev, int box_scale, int dtype,
+                        apb_stream_t stream) {
+  APB_CHECK_ARG(box_dev != nullptr && box_scale >= 1, APB_ERR_ARG, "flip_in_box_dev: box_dev/scale");
+  return flip_impl(x, y, B, H, W, C, 0, 0, 0, 0, box_dev, box_scale, dtype, APB_STREAM(stream));
+}
+
+static int flip_impl(const void* x, void* y, int B, int H, int W, int C, int r0, int c0, int r1, int c1, const int* box_dev,
+                     int box_scale, int dtype, cudaStream_t st) {
   APB_CHECK_ARG(x != y, APB_ERR_ARG, "flip_in_box: must be out of place");
   const long long n = (long long)B * H * W * C;
   if (n <= 0) return 0;
   const bool al = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
   if (dtype == APB_F32 && C % 4 == 0 && al) {
-    flip_in_box_kernel<float, 4><<<ew_grid(n / 4), EW_THREADS, 0, st>>>((const float*)x, (float*)y, B, H, W, C, r0, c0, r1, c1);
+    flip_in_box_kernel<float, 4><<<ew_grid(n / 4), EW_THREADS, 0, st>>>((const float*)x, (float*)y, B, H, W, C, r0, c0, r1, c1, box_dev, box_scale);
     APB_LAUNCH_CHECK("flip_in_box");
     return 0;
   }
   if (dtype == APB_BF16 && C % 8 == 0 && al) {
-    flip_in_box_kernel<bf16, 8><<<ew_grid(n / 8), EW_THREADS, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C, r0, c0, r1, c1);
+    flip_in_box_kernel<bf16, 8><<<ew_grid(n / 8), EW_THREADS, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C, r0, c0, r1, c1, box_dev, box_scale);
     APB_LAUNCH_CHECK("flip_in_box");
     return 0;
   }
   DISPATCH_T(dtype, "flip_in_box",
-             (flip_in_box_kernel<float, 1><<<ew_grid(n), EW_THREADS, 0, st>>>((const float*)x, (float*)y, B, H, W, C, r0, c0, r1, c1)),
-             (flip_in_box_kernel<bf16, 1><<<ew_grid(n), EW_THREADS, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C, r0, c0, r1, c1)));
+             (flip_in_box_kernel<float, 1><<<ew_grid(n), EW_THREADS, 0, st>>>((const float*)x, (float*)y, B, H, W, C, r0, c0, r1, c1, box_dev, box_scale)),
+             (flip_in_box_kernel<bf16, 1><<<ew_grid(n), EW_THREADS, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C, r0, c0, r1, c1, box_dev, box_scale)));
   return 0;
 }
 

@@ -180,6 +180,9 @@ int ln_bwd_v4_launch(const void* dy, const void* xs, const float* mean, const fl
                      int grid, long long rows, int C, int sdtype, int cdtype, cudaStream_t st);
 int colsum_v8_launch(const void* a, long long rows, int C, float* part, int rows_per_cta, int parts, int dtype,
                      cudaStream_t st);
+int ln_fwd_v4_launch(const void* x, const void* r, const float* rs, int rows_per_sample, const float* gamma, const float* beta,
+                     void* xs_out, void* y, float* mean, float* rstd, long long rows, int C, float eps, int sdtype, int cdtype,
+                     cudaStream_t st);
 
 #define LN_GRID_BWD (148 * 4)   // persistent CTAs of the backward kernel (<= this many partial rows)
 
@@ -194,6 +197,10 @@ int apb_ln_fwd(const void* x, const void* r, const float* rs, int rows_per_sampl
   if (rows <= 0) return 0;
   const int grid = ceil_div(rows, 8);
   const int nv = (C + 31) / 32;
+  if (ln_fwd_v4_launch(x, r, rs, rows_per_sample, gamma, beta, xs_out, y, mean, rstd, rows, C, eps, sdtype, cdtype, st) == 1) {
+    APB_LAUNCH_CHECK("ln_fwd_v4");
+    return 0;
+  }
 #define LN_FWD_NV(NV_, TS_, TC_)                                                                                  \
   ln_fwd_kernel<NV_, TS_, TC_, TC_><<<grid, 256, 0, st>>>((const TS_*)x, (const TC_*)r, rs, rows_per_sample, gamma, \
                                                            beta, (TS_*)xs_out, (TC_*)y, mean, rstd, rows, C, eps)

@@ -104,6 +104,63 @@ __global__ void __launch_bounds__(256) ln_bwd_v4_kernel(const TC* __restrict__ d
   }
 }
 
+// forward: xs = x + rs[b]*r ; y = LN(xs)*gamma + beta.  NG groups of 4 channels per lane, all loads up front.
+template <int NG, typename TS, typename TC>
+__global__ void __launch_bounds__(256) ln_fwd_v4_kernel(const TS* __restrict__ x, const TC* __restrict__ r,
+                                                        const float* __restrict__ rs, int rows_per_sample,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        TS* __restrict__ xs_out, TC* __restrict__ y,
+                                                        float* __restrict__ mean, float* __restrict__ rstd, long long rows,
+                                                        int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int ngroups = C >> 2;
+  const size_t base = (size_t)row * C;
+  int off[NG];
+  bool ok[NG];
+  float4 v[NG], rv[NG];
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+    const int g = k * 32 + lane;
+    ok[k] = g < ngroups;
+    off[k] = (ok[k] ? g : 0) * 4;
+    v[k] = ld4(x + base + off[k]);
+    rv[k] = r != nullptr ? ld4(r + base + off[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float s = (rs != nullptr) ? rs[row / rows_per_sample] : 1.f;
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+    if (r != nullptr) {
+      v[k].x = fmaf(s, rv[k].x, v[k].x); v[k].y = fmaf(s, rv[k].y, v[k].y);
+      v[k].z = fmaf(s, rv[k].z, v[k].z); v[k].w = fmaf(s, rv[k].w, v[k].w);
+    }
+    if (xs_out != nullptr && ok[k]) st4(xs_out + base + off[k], v[k]);
+    if (!ok[k]) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sum += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+  const float mu = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < NG; ++k)
+    if (ok[k]) {
+      const float a = v[k].x - mu, b = v[k].y - mu, c = v[k].z - mu, d = v[k].w - mu;
+      sq += fmaf(a, a, b * b) + fmaf(c, c, d * d);
+    }
+  const float rs_ = rsqrtf(warp_sum(sq) / (float)C + eps);
+  if (y != nullptr) {
+#pragma unroll
+    for (int k = 0; k < NG; ++k)
+      if (ok[k]) {
+        const float4 ga = ld4(gamma + off[k]), be = ld4(beta + off[k]);
+        st4(y + base + off[k], make_float4(fmaf((v[k].x - mu) * rs_, ga.x, be.x), fmaf((v[k].y - mu) * rs_, ga.y, be.y),
+                                           fmaf((v[k].z - mu) * rs_, ga.z, be.z), fmaf((v[k].w - mu) * rs_, ga.w, be.w)));
+      }
+  }
+  if (lane == 0 && mean != nullptr) { mean[row] = mu; rstd[row] = rs_; }
+}
+
 // column sums, stage 1: lane = 8 consecutive columns (16-byte loads for bf16), warp = 256 columns, warps stride the rows
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_v8_kernel(const T* __restrict__ a, long long rows, int C,
@@ -207,6 +264,35 @@ int ln_bwd_v4_launch(const void* dy, const void* xs, const float* mean, const fl
   else return 0;
 #undef V4_T
 #undef V4
+  return 1;
+}
+
+int ln_fwd_v4_launch(const void* x, const void* r, const float* rs, int rows_per_sample, const float* gamma, const float* beta,
+                     void* xs_out, void* y, float* mean, float* rstd, long long rows, int C, float eps, int sdtype, int cdtype,
+                     cudaStream_t st) {
+  if ((C & 3) != 0 || C > 1024) return 0;
+  const uintptr_t al = (uintptr_t)x | (uintptr_t)r | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)xs_out | (uintptr_t)y;
+  if (al & 15) return 0;
+  const int ng = (C / 4 + 31) / 32;
+  const int grid = ceil_div(rows, 8);
+#define F4(NG_, TS_, TC_)                                                                                            \
+  ln_fwd_v4_kernel<NG_, TS_, TC_><<<grid, 256, 0, st>>>((const TS_*)x, (const TC_*)r, rs, rows_per_sample, gamma, beta, \
+                                                        (TS_*)xs_out, (TC_*)y, mean, rstd, rows, C, eps)
+#define F4_T(TS_, TC_)                  \
+  do {                                  \
+    if (ng <= 1) F4(1, TS_, TC_);       \
+    else if (ng <= 2) F4(2, TS_, TC_);  \
+    else if (ng <= 3) F4(3, TS_, TC_);  \
+    else if (ng <= 4) F4(4, TS_, TC_);  \
+    else if (ng <= 6) F4(6, TS_, TC_);  \
+    else F4(8, TS_, TC_);               \
+  } while (0)
+  if (sdtype == APB_F32 && cdtype == APB_F32) F4_T(float, float);
+  else if (sdtype == APB_F32 && cdtype == APB_BF16) F4_T(float, bf16);
+  else if (sdtype == APB_BF16 && cdtype == APB_BF16) F4_T(bf16, bf16);
+  else return 0;
+#undef F4_T
+#undef F4
   return 1;
 }
 

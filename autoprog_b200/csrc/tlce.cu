@@ -26,6 +26,7 @@ struct TlceParams {
   long long t_sb, t_sc, t_ss;  // target strides (batch, class, slot); 2-D target: (C, 1, 0)
   int slot_cls, slot_aux0;     // 3-D: 1, 2   2-D: 0, 0
   float lam;                   // cls-target mix factor (>= 1 -> no mixing)
+  const int* box_dev;          // optional device (bbx1,bby1,bbx2,bby2): overrides lam (CUDA-graph path)
   float w_cls, w_dense;        // already divided by B and B*N
   int tiles_per_img;
 };
@@ -99,7 +100,10 @@ __global__ void __launch_bounds__(NTHREADS) tlce_kernel(TlceParams p) {
       T* dr = reinterpret_cast<T*>(p.d_cls) + (size_t)b * C;
       const float* t0 = p.target + (size_t)b * p.t_sb + (size_t)p.slot_cls * p.t_ss;
       const float* t1 = p.target + (size_t)(p.B - 1 - b) * p.t_sb + (size_t)p.slot_cls * p.t_ss;
-      const bool mix = p.lam < 1.f;
+      float lam = p.lam;
+      if (p.box_dev != nullptr)
+        lam = 1.f - (float)((p.box_dev[2] - p.box_dev[0]) * (p.box_dev[3] - p.box_dev[1])) / (float)p.N;
+      const bool mix = lam < 1.f;
       float m = -INFINITY;
       for (int c = lane; c < C; c += 32) m = fmaxf(m, to_f(xr[c]));
       m = warp_max(m);
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(NTHREADS) tlce_kernel(TlceParams p) {
       for (int c = lane; c < C; c += 32) {
         const float x = to_f(xr[c]);
         float t = t0[(size_t)c * p.t_sc];
-        if (mix) t = p.lam * t + (1.f - p.lam) * t1[(size_t)c * p.t_sc];
+        if (mix) t = lam * t + (1.f - lam) * t1[(size_t)c * p.t_sc];
         se += expf(x - m);
         sum_t += t;
         sum_tx = fmaf(t, x, sum_tx);
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(NTHREADS) tlce_kernel(TlceParams p) {
       for (int c = lane; c < C; c += 32) {
         const float x = to_f(xr[c]);
         float t = t0[(size_t)c * p.t_sc];
-        if (mix) t = p.lam * t + (1.f - p.lam) * t1[(size_t)c * p.t_sc];
+        if (mix) t = lam * t + (1.f - lam) * t1[(size_t)c * p.t_sc];
         dr[c] = from_f<T>(p.w_cls * (expf(x - lse) * sum_t - t));
       }
     }
@@ -163,8 +167,8 @@ long long apb_tlce_workspace_floats(int B, int N) {
 }
 
 int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, int target_is_3d, int B, int N, int C,
-                     int box_area, float w_cls, float w_dense, float* loss, void* d_cls, void* d_aux, float* workspace,
-                     int dtype, apb_stream_t stream) {
+                     int box_area, const int* box_dev, float w_cls, float w_dense, float* loss, void* d_cls, void* d_aux,
+                     float* workspace, int dtype, apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
   APB_CHECK_ARG(B > 0 && N > 0 && C > 0, APB_ERR_SHAPE, "tlce: bad shape B=%d N=%d C=%d", B, N, C);
   APB_CHECK_ARG(dtype == APB_F32 || dtype == APB_BF16, APB_ERR_DTYPE, "tlce: dtype %d", dtype);
@@ -174,6 +178,7 @@ int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, 
   if (target_is_3d) { p.t_sb = (long long)C * (2 + N); p.t_sc = 2 + N; p.t_ss = 1; p.slot_cls = 1; p.slot_aux0 = 2; }
   else { p.t_sb = C; p.t_sc = 1; p.t_ss = 0; p.slot_cls = 0; p.slot_aux0 = 0; }
   p.lam = 1.f - (float)((double)box_area / (double)N);
+  p.box_dev = box_dev;
   p.w_cls = w_cls / (float)B;
   p.w_dense = w_dense / ((float)B * (float)N);
   p.tiles_per_img = (N + TT - 1) / TT;

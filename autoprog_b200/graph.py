@@ -1,0 +1,76 @@
+"""Whole-step CUDA-graph capture of the training hot path.
+
+The reference launches ~1300 kernels per step from Python and synchronises every step (main_prog.py:1035); at the
+early AutoProg stages (128-160 px, depth 9-12) the GPU work per step is shorter than the host's launch time.  A
+`GraphedTrainStep` captures zero-grad + forward + loss + backward + fused optimizer/EMA step ONCE per (resolution,
+depth, batch) configuration and replays it.  Everything that changes between steps is read from memory at replay
+time: the mix-token box (host RNG -> pinned int32[4] -> device, read by the flip and loss kernels), the optimizer's
+lr / bias corrections (pinned -> device), DropPath masks (CUDA RNG is graph-safe), inputs (static buffers).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .volo import rand_bbox
+
+
+class GraphedTrainStep:
+    def __init__(self, model, criterion, optimizer, example_input, example_target, bf16: bool = True, warmup: int = 3):
+        self.model, self.criterion, self.optimizer, self.bf16 = model, criterion, optimizer, bf16
+        self.net = model.module if hasattr(model, 'module') else model
+        dev = example_input.device
+        self.x = example_input.clone()
+        self.t = example_target.clone()
+        self.box_host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.box_dev = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.net._graph_box, self.net._graph_box_host = self.box_dev, self.box_host
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._host_prepare()
+                self._device_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._host_prepare()
+        from . import kernels as K
+        n0 = K.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._device_step()
+        self.kernels_per_step = K.launch_count() - n0      # launches of this library captured in the graph
+
+    def _host_prepare(self):
+        net = self.net
+        if getattr(net, 'mix_token', False) and net.training:
+            lam = np.random.beta(net.beta, net.beta)
+            s = net.pooling_scale
+            g = self.x.shape[-1] // 8                      # stage-1 token grid
+            box = rand_bbox((self.x.shape[0], g, g, 0), lam, scale=s)
+            self.box_host.copy_(torch.tensor([int(v) for v in box], dtype=torch.int32))
+        self.optimizer.prepare_step()
+
+    def _device_step(self):
+        self.box_dev.copy_(self.box_host, non_blocking=True)
+        self.optimizer.zero_grad()
+        with ops.autocast(enabled=self.bf16):
+            out = self.model(self.x)
+            loss = self.criterion(out, self.t)
+        loss.backward()
+        self.optimizer.launch_step()
+        self.optimizer.update_ema_buffers()
+        return loss.detach()
+
+    def __call__(self, x=None, target=None):
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        if target is not None:
+            self.t.copy_(target, non_blocking=True)
+        self._host_prepare()
+        self.graph.replay()
+        return self.loss
+
+    def close(self):
+        self.net._graph_box = None

@@ -60,7 +60,7 @@ def outlook_bwd(v, logits, dy, heads: int, scale: float, simt: bool = False) -> 
 
 
 # ------------------------------------------------------------------ token-label CE
-def tlce_fwd_bwd(x_cls, x_aux, target, box_area: int, w_cls: float, w_dense: float):
+def tlce_fwd_bwd(x_cls, x_aux, target, box_area: int, w_cls: float, w_dense: float, box_dev=None):
     B, N, Cc = x_aux.shape
     assert x_cls.shape == (B, Cc) and x_cls.dtype == x_aux.dtype
     assert target.dtype == torch.float32
@@ -70,7 +70,7 @@ def tlce_fwd_bwd(x_cls, x_aux, target, box_area: int, w_cls: float, w_dense: flo
     d_cls = torch.empty_like(x_cls)
     d_aux = torch.empty_like(x_aux)
     ws = torch.empty(int(lib().apb_tlce_workspace_floats(B, N)), device=x_aux.device, dtype=torch.float32)
-    check(lib().apb_tlce_fwd_bwd(_p(x_cls), _p(x_aux), _p(target), int(is3d), B, N, Cc, int(box_area), w_cls, w_dense,
+    check(lib().apb_tlce_fwd_bwd(_p(x_cls), _p(x_aux), _p(target), int(is3d), B, N, Cc, int(box_area), _p(box_dev), w_cls, w_dense,
                                  _p(loss), _p(d_cls), _p(d_aux), _p(ws), dt(x_aux), _st()), 'tlce_fwd_bwd')
     return loss, d_cls, d_aux
 
@@ -230,6 +230,15 @@ def flip_in_box(x, box: Sequence[int]):
     y = torch.empty_like(x)
     r0, c0, r1, c1 = [int(b) for b in box]
     check(lib().apb_flip_in_box(_p(x), _p(y), B, H, W, Cc, r0, c0, r1, c1, dt(x), _st()), 'flip_in_box')
+    return y
+
+
+def flip_in_box_dev(x, box_dev, scale: int):
+    """Same as flip_in_box with the box (r0,c0,r1,c1) read from a device int32[4] tensor and multiplied by `scale`."""
+    B, H, W, Cc = x.shape
+    y = torch.empty_like(x)
+    assert box_dev.dtype == torch.int32 and box_dev.numel() == 4
+    check(lib().apb_flip_in_box_dev(_p(x), _p(y), B, H, W, Cc, _p(box_dev), int(scale), dt(x), _st()), 'flip_in_box_dev')
     return y
 
 

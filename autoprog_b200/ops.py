@@ -264,6 +264,27 @@ class FlipInBoxFn(torch.autograd.Function):
         return K.flip_in_box(_c(dy), ctx.box), None
 
 
+class DevBox(tuple):
+    """(bbx1, bby1, bbx2, bby2) whose live values sit in a device int32[4] tensor (`.dev`); the tuple entries are the
+    values seen when the step was captured into a CUDA graph.  Returned by VOLO.forward in graph mode."""
+
+    def __new__(cls, values, dev):
+        obj = super().__new__(cls, values)
+        obj.dev = dev
+        return obj
+
+
+class FlipInBoxDevFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, box_dev, scale):
+        ctx.box, ctx.scale = box_dev, scale
+        return K.flip_in_box_dev(_c(x), box_dev, scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.flip_in_box_dev(_c(dy), ctx.box, ctx.scale), None, None
+
+
 class PatchConvFn(torch.autograd.Function):
     """Conv2d(kernel=p, stride=p) on an NHWC tensor as patchify + GEMM (models/volo.py:370-373, 389)."""
 
@@ -386,15 +407,15 @@ class TokenLabelCEFn(torch.autograd.Function):
     """Fused TokenLabelCrossEntropy forward+gradient (loss/cross_entropy.py:136-156)."""
 
     @staticmethod
-    def forward(ctx, x_cls, x_aux, target, box_area, w_cls, w_dense):
-        loss, d_cls, d_aux = K.tlce_fwd_bwd(_c(x_cls), _c(x_aux), _c(target), box_area, w_cls, w_dense)
+    def forward(ctx, x_cls, x_aux, target, box_area, w_cls, w_dense, box_dev=None):
+        loss, d_cls, d_aux = K.tlce_fwd_bwd(_c(x_cls), _c(x_aux), _c(target), box_area, w_cls, w_dense, box_dev)
         ctx.save_for_backward(d_cls, d_aux)
         return loss
 
     @staticmethod
     def backward(ctx, g):
         d_cls, d_aux = ctx.saved_tensors
-        return K.scale_by_scalar(d_cls, g), K.scale_by_scalar(d_aux, g), None, None, None, None
+        return K.scale_by_scalar(d_cls, g), K.scale_by_scalar(d_aux, g), None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------

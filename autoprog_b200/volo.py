@@ -537,7 +537,12 @@ class VOLO(nn.Module):
             raise RuntimeError('autoprog_b200.VOLO runs on CUDA (sm_100a) only; there is no CPU fallback')
         x = self.forward_embeddings(x)
 
-        if self.mix_token and self.training:
+        graph_box = getattr(self, '_graph_box', None)      # set by graph.GraphedTrainStep: device-resident bbox
+        if self.mix_token and self.training and graph_box is not None:
+            patch_h, patch_w = x.shape[1] // self.pooling_scale, x.shape[2] // self.pooling_scale
+            bbx1, bby1, bbx2, bby2 = (int(v) for v in self._graph_box_host.tolist())
+            x = ops.FlipInBoxDevFn.apply(x, graph_box, self.pooling_scale)
+        elif self.mix_token and self.training:
             lam = np.random.beta(self.beta, self.beta)
             patch_h, patch_w = x.shape[1] // self.pooling_scale, x.shape[2] // self.pooling_scale
             bbx1, bby1, bbx2, bby2 = (int(v) for v in rand_bbox(x.size(), lam, scale=self.pooling_scale))
@@ -561,6 +566,10 @@ class VOLO(nn.Module):
             return x_cls + 0.5 * x_aux.max(1)[0]
         if self.mix_token and self.training:
             B, _, ncls = x_aux.shape
+            if graph_box is not None:
+                x_aux = ops.FlipInBoxDevFn.apply(x_aux.reshape(B, patch_h, patch_w, ncls), graph_box, 1)
+                x_aux = x_aux.reshape(B, patch_h * patch_w, ncls)
+                return x_cls, x_aux, ops.DevBox((bbx1, bby1, bbx2, bby2), graph_box)
             x_aux = ops.FlipInBoxFn.apply(x_aux.reshape(B, patch_h, patch_w, ncls), (bbx1, bby1, bbx2, bby2))
             x_aux = x_aux.reshape(B, patch_h * patch_w, ncls)
         return x_cls, x_aux, (bbx1, bby1, bbx2, bby2)

@@ -39,6 +39,7 @@ def parse():
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--fp32', action='store_true', help='fp32 parity mode (CUDA-core kernels)')
+    ap.add_argument('--no-graph', action='store_true', help='do not replay the step from a CUDA graph')
     return ap.parse_args()
 
 
@@ -182,6 +183,23 @@ def main():
     x_dev = torch.randn(B, 3, res, res, device=dev)
     t_dev = torch.softmax(torch.randn(B, 1000, 2 + g * g, device=dev), dim=1)
 
+    # whole-step CUDA graph (single GPU): zero-grad + fwd + loss + bwd + optimizer/EMA captured once, replayed per step;
+    # the mix-token box and lr / bias corrections are read from memory at replay time (autoprog_b200/graph.py)
+    graphed, graph_note = None, 'eager launches'
+    if world == 1 and not args.no_graph:
+        try:
+            from autoprog_b200.graph import GraphedTrainStep
+            graphed = GraphedTrainStep(net, crit, opt, x_dev, t_dev, bf16=bf16, warmup=3)
+            graph_note = 'whole step replayed from one CUDA graph'
+        except Exception as e:   # noqa: BLE001 - fall back to eager launches, say so in the JSON line
+            graphed, graph_note = None, f'eager launches (graph capture failed: {type(e).__name__}: {str(e)[:80]})'
+            model._graph_box = None
+
+    def run_step(x, tgt):
+        if graphed is not None:
+            return graphed(x if x is not x_dev else None, tgt if tgt is not t_dev else None)
+        return train_step(x, tgt)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -202,13 +220,15 @@ def main():
 
     # ---- device-resident arm ----------------------------------------------------------------------------------
     for _ in range(max(3, args.warmup)):
-        train_step(x_dev, t_dev)
+        run_step(x_dev, t_dev)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = K.launch_count()
-    ms = timed(lambda: train_step(x_dev, t_dev), args.steps)
+    ms = timed(lambda: run_step(x_dev, t_dev), args.steps)
     launches = K.launch_count() - l0
+    if graphed is not None:
+        launches = graphed.kernels_per_step * args.steps      # replayed from the graph: counted at capture time
     clocks = sampler.stop() if rank == 0 else None
     value = B * world * args.steps / (ms / 1e3)
 
@@ -235,7 +255,7 @@ def main():
             slot = state['i'] & 1
             torch.cuda.current_stream().wait_event(ready[slot])
             prefetch(slot ^ 1)                      # next batch streams in while this step computes (tlt PrefetchLoader)
-            loss = train_step(dx[slot], dtg[slot])
+            loss = run_step(dx[slot], dtg[slot])
             consumed[slot].record()
             state['loss'] = float(loss.item())      # D2H of the step's result
             state['i'] += 1
@@ -253,6 +273,9 @@ def main():
     # ---- roofline of the dominant kernel (tcgen05 GEMM), in situ: one extra step with every GEMM launch bracketed by events
     roof = None
     extra = {}
+    if graphed is not None:
+        graphed.close()              # the instrumented roofline step below runs eagerly
+        launches_per_step_eager = None
     if rank == 0:
         # rank-local extra step: no collective may be issued here (the other ranks do not take part)
         if world > 1:
@@ -273,7 +296,7 @@ def main():
             'warmup': max(3, args.warmup), 'ms_per_step': round(ms / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'bf16' if bf16 else 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'model': args.model, 'res': res, 'per_gpu_batch': B, 'global_batch': B * world,
-                       'parallelism': f'dp{world}', 'optimizer': f'fused AdamW + {len(decays)} EMA', 'drop_path': 0.1,
+                       'parallelism': f'dp{world}', 'optimizer': f'fused AdamW + {len(decays)} EMA', 'drop_path': 0.1, 'launch': graph_note,
                        'l2': 'per-step working set (activations ~7 GB) exceeds the 126 MB L2; no explicit flush'},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
         }

@@ -51,8 +51,10 @@ int apb_outlook_bwd(const void* v, const void* logits, const void* dy, void* dv,
  * workspace: apb_tlce_workspace_floats(B,N) floats. */
 long long apb_tlce_workspace_floats(int B, int N);
 int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, int target_is_3d, int B, int N, int C,
-                     int box_area, float w_cls, float w_dense, float* loss, void* d_cls, void* d_aux, float* workspace,
-                     int dtype, apb_stream_t stream);
+                     int box_area, const int* box_dev, float w_cls, float w_dense, float* loss, void* d_cls, void* d_aux,
+                     float* workspace, int dtype, apb_stream_t stream);
+/* box_dev: optional DEVICE int[4] (bbx1,bby1,bbx2,bby2) read by the kernel instead of box_area, so a captured CUDA
+ * graph sees a fresh mix-token box on every replay. */
 int apb_scale_by_scalar(const void* in, void* out, long long n, const float* scalar, int dtype, apb_stream_t stream);
 
 /* ---- fused residual add (+DropPath per-sample scale) + LayerNorm  (models/volo.py:142-143, 232-233, 306-307)
@@ -123,6 +125,8 @@ int apb_avgpool2_fwd(const void* x, void* y, int B, int H, int W, int C, int dty
 int apb_avgpool2_bwd(const void* dy, void* dx, int B, int H, int W, int C, int accumulate, int dtype, apb_stream_t stream);
 int apb_flip_in_box(const void* x, void* y, int B, int H, int W, int C, int r0, int c0, int r1, int c1, int dtype,
                     apb_stream_t stream);
+int apb_flip_in_box_dev(const void* x, void* y, int B, int H, int W, int C, const int* box_dev, int box_scale, int dtype,
+                        apb_stream_t stream);   /* box (r0,c0,r1,c1) * box_scale read from device memory */
 int apb_patchify(const void* x, void* rows, int B, int H, int W, int C, int p, int dtype, apb_stream_t stream);
 int apb_unpatchify(const void* rows, void* x, int B, int H, int W, int C, int p, int dtype, apb_stream_t stream);
 int apb_bicubic_resize(const float* src, float* dst, int h, int w, int h0, int w0, int C, apb_stream_t stream);
