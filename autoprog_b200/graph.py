@@ -34,7 +34,7 @@ class GraphedTrainStep:
                 self._device_step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self._host_prepare()
+        # capture only records: no host state (RNG, optimizer step count) is advanced for it
         from . import kernels as K
         n0 = K.launch_count()
         self.graph = torch.cuda.CUDAGraph()

@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--fp32', action='store_true', help='fp32 parity mode (CUDA-core kernels)')
     ap.add_argument('--no-graph', action='store_true', help='do not replay the step from a CUDA graph')
+    ap.add_argument('--no-stages', action='store_true', help='skip the per-stage AutoProg schedule table (N=1 only)')
     return ap.parse_args()
 
 
@@ -285,6 +286,33 @@ def main():
             roof, extra = measure_rooflines(train_step, x_dev, t_dev, K, torch, B, bf16)
     barrier()
 
+    # ---- the earlier AutoProg stages of the same schedule (scripts/train_autoprog.sh -> progressive_schedule):
+    #      (depth, resolution, drop-path) = (9,128,0) (12,160,.033) (15,192,.067); reported as extra information
+    stages = None
+    if rank == 0 and world == 1 and not args.no_stages and args.model == 'volo_d1' and not args.fp32:
+        stages = [{'l': 18, 'r': res, 'images_per_s': round(value, 1)}]
+        del model, emas, opt, net
+        torch.cuda.empty_cache()
+        for l, r, dp in ((9, 128, 0.0), (12, 160, 0.1 / 3), (15, 192, 0.2 / 3)):
+            try:
+                sm = A.create_model('model_variant', variant=f'volo_h12_l{l}', img_size=224, drop_path_rate=dp).to(dev)
+                se = [copy.deepcopy(sm).eval() for _ in decays]
+                so = FusedAdamW(sm, lr=1e-3, weight_decay=0.05, ema_models=se, ema_decays=decays)
+                sx = torch.randn(B, 3, r, r, device=dev)
+                st = torch.softmax(torch.randn(B, 1000, 2 + (r // 16) ** 2, device=dev), dim=1)
+                from autoprog_b200.graph import GraphedTrainStep
+                gs = GraphedTrainStep(sm, crit, so, sx, st, bf16=True, warmup=3)
+                for _ in range(3):
+                    gs()
+                sms = timed(lambda: gs(), args.steps)
+                stages.append({'l': l, 'r': r, 'images_per_s': round(B * args.steps / (sms / 1e3), 1)})
+                gs.close()
+                del sm, se, so, gs, sx, st
+                torch.cuda.empty_cache()
+            except Exception as e:   # noqa: BLE001
+                stages.append({'l': l, 'r': r, 'error': f'{type(e).__name__}: {str(e)[:80]}'})
+        stages.sort(key=lambda d: d['l'])
+
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         v, cores, sample = cpu_path_images_per_sec(args.cpu_steps, 1, args.model, args.res)
@@ -301,6 +329,8 @@ def main():
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
         }
         line.update(extra)
+        if stages is not None:
+            line['autoprog_stages'] = stages
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
