@@ -365,8 +365,11 @@ def measure_rooflines(train_step, x, t, K, torch, B, bf16):
     K.outlook_bwd = wrap('outlook_bwd', lambda v, lg, *a, **kw: (3 * v.numel() + 2 * lg.numel()) * es)
     K.tlce_fwd_bwd = wrap('tlce', lambda xc, xa, *a, **kw: xa.numel() * (2 * es + 4))
     try:
-        train_step(x, t)
-        torch.cuda.synchronize()
+        for _ in range(2):            # first pass warms the caching allocator (host stalls would inflate event spans)
+            for v in rec.values():
+                v.clear()
+            train_step(x, t)
+            torch.cuda.synchronize()
     finally:
         K.gemm, K.outlook_fwd, K.outlook_bwd, K.tlce_fwd_bwd = orig['gemm'], orig['outlook_fwd'], orig['outlook_bwd'], orig['tlce']
 
