@@ -154,6 +154,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ.setdefault('TORCH_NCCL_ASYNC_ERROR_HANDLING', '0')   # the watchdog must not poll a capturing stream
         dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(0)
     np.random.seed(0 + rank)
@@ -187,7 +188,7 @@ def main():
     # whole-step CUDA graph (single GPU): zero-grad + fwd + loss + bwd + optimizer/EMA captured once, replayed per step;
     # the mix-token box and lr / bias corrections are read from memory at replay time (autoprog_b200/graph.py)
     graphed, graph_note = None, 'eager launches'
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         try:
             from autoprog_b200.graph import GraphedTrainStep
             graphed = GraphedTrainStep(net, crit, opt, x_dev, t_dev, bf16=bf16, warmup=3)
@@ -195,6 +196,13 @@ def main():
         except Exception as e:   # noqa: BLE001 - fall back to eager launches, say so in the JSON line
             graphed, graph_note = None, f'eager launches (graph capture failed: {type(e).__name__}: {str(e)[:80]})'
             model._graph_box = None
+        if world > 1:            # all ranks must take the same path
+            ok = torch.tensor([1 if graphed is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0 and graphed is not None:
+                graphed.close()
+                graphed, graph_note = None, 'eager launches (graph capture failed on another rank)'
+                model._graph_box = None
 
     def run_step(x, tgt):
         if graphed is not None:
