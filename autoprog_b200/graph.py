@@ -17,9 +17,14 @@ from .volo import rand_bbox
 
 
 class GraphedTrainStep:
+    """Single GPU: one graph for the whole step.  Under `DistributedDataParallel` (autoprog_b200.ddp) the step is two
+    graphs -- [zero-grad, forward, loss, backward] and [optimizer + EMA] -- with the bucketed NCCL all-reduce of the
+    flat gradient buffers issued eagerly in between (NCCL collectives are kept out of the captured region)."""
+
     def __init__(self, model, criterion, optimizer, example_input, example_target, bf16: bool = True, warmup: int = 3):
         self.model, self.criterion, self.optimizer, self.bf16 = model, criterion, optimizer, bf16
         self.net = model.module if hasattr(model, 'module') else model
+        self.ddp = model if (hasattr(model, 'reduce_now') and getattr(model, 'world', 1) > 1) else None
         dev = example_input.device
         self.x = example_input.clone()
         self.t = example_target.clone()
@@ -38,9 +43,17 @@ class GraphedTrainStep:
         from . import kernels as K
         n0 = K.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._device_step()
-        self.kernels_per_step = K.launch_count() - n0      # launches of this library captured in the graph
+        self.graph_opt = None
+        if self.ddp is None:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._device_step()
+        else:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._fwd_bwd()
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
+                self._opt_step()
+        self.kernels_per_step = K.launch_count() - n0      # launches of this library captured in the graph(s)
 
     def _host_prepare(self):
         net = self.net
@@ -52,16 +65,29 @@ class GraphedTrainStep:
             self.box_host.copy_(torch.tensor([int(v) for v in box], dtype=torch.int32))
         self.optimizer.prepare_step()
 
-    def _device_step(self):
+    def _fwd_bwd(self):
         self.box_dev.copy_(self.box_host, non_blocking=True)
         self.optimizer.zero_grad()
         with ops.autocast(enabled=self.bf16):
             out = self.model(self.x)
             loss = self.criterion(out, self.t)
-        loss.backward()
+        if self.ddp is not None:
+            with self.ddp.no_sync():          # gradients are reduced outside the captured region
+                loss.backward()
+        else:
+            loss.backward()
+        return loss.detach()
+
+    def _opt_step(self):
         self.optimizer.launch_step()
         self.optimizer.update_ema_buffers()
-        return loss.detach()
+
+    def _device_step(self):
+        loss = self._fwd_bwd()
+        if self.ddp is not None:
+            self.ddp.reduce_now()
+        self._opt_step()
+        return loss
 
     def __call__(self, x=None, target=None):
         if x is not None:
@@ -70,6 +96,9 @@ class GraphedTrainStep:
             self.t.copy_(target, non_blocking=True)
         self._host_prepare()
         self.graph.replay()
+        if self.graph_opt is not None:
+            self.ddp.reduce_now()
+            self.graph_opt.replay()
         return self.loss
 
     def close(self):
