@@ -14,8 +14,8 @@
 
 namespace {
 
-constexpr int D = 32;
-constexpr int ROWP = 40;   // padded smem row pitch in bf16 (80 B): conflict-free ldmatrix
+// head dim D is a template parameter (32: every VOLO variant; 64: DeiT).  Shared-memory row pitch = D + 8 bf16
+// (80 / 144 bytes): ldmatrix rows of 8 consecutive keys fall into distinct bank groups.
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -51,9 +51,11 @@ __device__ __forceinline__ float quad_sum(float v) {
 }
 
 // rows [0,N) of a [N, 32] bf16 matrix with global row stride `gstride` (elements) -> smem [rows_pad][ROWP], tail zeroed
+template <int D>
 __device__ __forceinline__ void stage_rows(bf16* s, const bf16* g, size_t gstride, int N, int rows_pad) {
-  for (int e = threadIdx.x; e < rows_pad * 4; e += blockDim.x) {
-    const int n = e >> 2, ch = e & 3;
+  constexpr int ROWP = D + 8, CPR = D / 8;
+  for (int e = threadIdx.x; e < rows_pad * CPR; e += blockDim.x) {
+    const int n = e / CPR, ch = e % CPR;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (n < N) v = *reinterpret_cast<const uint4*>(g + (size_t)n * gstride + ch * 8);
     *reinterpret_cast<uint4*>(s + n * ROWP + ch * 8) = v;
@@ -61,10 +63,11 @@ __device__ __forceinline__ void stage_rows(bf16* s, const bf16* g, size_t gstrid
 }
 
 // A-operand fragments (16 rows x 32 channels = 2 k-steps) straight from global; rows >= N read as zero
-__device__ __forceinline__ void load_a_rows(uint32_t (&a)[2][4], const bf16* g, size_t gstride, int row0, int N, int lane) {
+template <int D>
+__device__ __forceinline__ void load_a_rows(uint32_t (&a)[D / 16][4], const bf16* g, size_t gstride, int row0, int N, int lane) {
   const int gi = lane >> 2, q = lane & 3;
 #pragma unroll
-  for (int ks = 0; ks < 2; ++ks)
+  for (int ks = 0; ks < D / 16; ++ks)
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       const int r = row0 + gi + (h & 1) * 8;
@@ -76,55 +79,64 @@ __device__ __forceinline__ void load_a_rows(uint32_t (&a)[2][4], const bf16* g, 
 // Per-lane ldmatrix byte offsets inside a [rows][ROWP] bf16 tile (loop invariant; all smem addressing is 32-bit):
 //   offT : "rows^T" pattern -- 8 rows x 4 channel chunks (B operand "col" of S = A . M^T)
 //   offR : "rows" pattern   -- 16 rows x 2 channel chunks, used with ldmatrix.trans (B operand of O = P . M)
-__device__ __forceinline__ uint32_t lane_offT(int lane) { return (uint32_t)(((lane & 7) * ROWP + (lane >> 3) * 8) * 2); }
+template <int D>
+__device__ __forceinline__ uint32_t lane_offT(int lane) { return (uint32_t)(((lane & 7) * (D + 8) + (lane >> 3) * 8) * 2); }
+template <int D>
 __device__ __forceinline__ uint32_t lane_offR(int lane) {
   const int mi = lane >> 3, r = lane & 7;
-  return (uint32_t)((((mi & 1) * 8 + r) * ROWP + (mi >> 1) * 8) * 2);
-}
-constexpr uint32_t ROWB = ROWP * 2;   // row pitch in bytes
-
-// S[16 x 8] (+)= A[16 x 32] . M[key0..key0+7][0..31]^T ; addr = tile + key0*ROWB + lane_offT
-__device__ __forceinline__ void mma_rowsT(float (&c)[4], const uint32_t (&a)[2][4], uint32_t addr) {
-  uint32_t b[4];
-  ldsm_x4(b, addr);
-  mma16816(c, a[0], b[0], b[1]);
-  mma16816(c, a[1], b[2], b[3]);
+  return (uint32_t)((((mi & 1) * 8 + r) * (D + 8) + (mi >> 1) * 8) * 2);
 }
 
-// O[16 x 32] += P[16 x 16 (keys key0..+15)] . M[key0..key0+15][0..31] ; addr = tile + key0*ROWB + lane_offR
-__device__ __forceinline__ void mma_rows(float (&o)[4][4], const uint32_t (&pa)[4], uint32_t addr) {
-  uint32_t b[4];
-  ldsm_x4_t(b, addr);
-  mma16816(o[0], pa, b[0], b[1]);
-  mma16816(o[1], pa, b[2], b[3]);
-  ldsm_x4_t(b, addr + 32);
-  mma16816(o[2], pa, b[0], b[1]);
-  mma16816(o[3], pa, b[2], b[3]);
+// S[16 x 8] (+)= A[16 x D] . M[key0..key0+7][0..D)^T ; addr = tile + key0*ROWB + lane_offT
+template <int D>
+__device__ __forceinline__ void mma_rowsT(float (&c)[4], const uint32_t (&a)[D / 16][4], uint32_t addr) {
+#pragma unroll
+  for (int k2 = 0; k2 < D / 32; ++k2) {
+    uint32_t b[4];
+    ldsm_x4(b, addr + k2 * 64);
+    mma16816(c, a[2 * k2], b[0], b[1]);
+    mma16816(c, a[2 * k2 + 1], b[2], b[3]);
+  }
 }
 
-__global__ void __launch_bounds__(256, 3) mhsa_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+// O[16 x D] += P[16 x 16 (keys key0..+15)] . M[key0..key0+15][0..D) ; addr = tile + key0*ROWB + lane_offR
+template <int D>
+__device__ __forceinline__ void mma_rows(float (&o)[D / 8][4], const uint32_t (&pa)[4], uint32_t addr) {
+#pragma unroll
+  for (int half = 0; half < D / 16; ++half) {
+    uint32_t b[4];
+    ldsm_x4_t(b, addr + half * 32);
+    mma16816(o[2 * half], pa, b[0], b[1]);
+    mma16816(o[2 * half + 1], pa, b[2], b[3]);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256, (D == 32 ? 3 : 1)) mhsa_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                            float* __restrict__ lse, int N, int heads, float scale,
                                                            int rows_pad) {
+  constexpr int ROWP = D + 8;
+  constexpr uint32_t ROWB = ROWP * 2;
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* sK = reinterpret_cast<bf16*>(smraw);
   bf16* sV = sK + (size_t)rows_pad * ROWP;
   const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
   const size_t tok = (size_t)3 * heads * D;
   const bf16* qb = qkv + (size_t)b * N * tok + (size_t)hd * D;
-  stage_rows(sK, qb + heads * D, tok, N, rows_pad);
-  stage_rows(sV, qb + 2 * heads * D, tok, N, rows_pad);
+  stage_rows<D>(sK, qb + heads * D, tok, N, rows_pad);
+  stage_rows<D>(sV, qb + 2 * heads * D, tok, N, rows_pad);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int gi = lane >> 2, q = lane & 3;
   const float sl2 = scale * 1.4426950408889634f;
-  const uint32_t sK_T = smem_u32(sK) + lane_offT(lane), sV_R = smem_u32(sV) + lane_offR(lane);
+  const uint32_t sK_T = smem_u32(sK) + lane_offT<D>(lane), sV_R = smem_u32(sV) + lane_offR<D>(lane);
   const int nfull = N / 64;                 // key blocks that need no masking
   for (int row0 = warp * 16; row0 < N; row0 += nwarp * 16) {
-    uint32_t qa[2][4];
-    load_a_rows(qa, qb, tok, row0, N, lane);
-    float o[4][4];
+    uint32_t qa[D / 16][4];
+    load_a_rows<D>(qa, qb, tok, row0, N, lane);
+    float o[D / 8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < D / 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
@@ -135,7 +147,7 @@ __global__ void __launch_bounds__(256, 3) mhsa_fwd_mma_kernel(const bf16* __rest
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
         s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
-        if (!tail || k0 + nb * 8 < N) mma_rowsT(s[nb], qa, sK_T + (uint32_t)(k0 + nb * 8) * ROWB);
+        if (!tail || k0 + nb * 8 < N) mma_rowsT<D>(s[nb], qa, sK_T + (uint32_t)(k0 + nb * 8) * ROWB);
       }
       if (tail) {
 #pragma unroll
@@ -159,7 +171,7 @@ __global__ void __launch_bounds__(256, 3) mhsa_fwd_mma_kernel(const bf16* __rest
         l_run[h] *= corr[h];
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1]; }
+      for (int i = 0; i < D / 8; ++i) { o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1]; }
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(256, 3) mhsa_fwd_mma_kernel(const bf16* __rest
         if (!tail || k0 + kk * 16 < N) {
           const uint32_t pa[4] = {pack_bf16(s[2 * kk][0], s[2 * kk][1]), pack_bf16(s[2 * kk][2], s[2 * kk][3]),
                                   pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3])};
-          mma_rows(o, pa, sV_R + (uint32_t)(k0 + kk * 16) * ROWB);
+          mma_rows<D>(o, pa, sV_R + (uint32_t)(k0 + kk * 16) * ROWB);
         }
       }
     }
@@ -185,7 +197,7 @@ __global__ void __launch_bounds__(256, 3) mhsa_fwd_mma_kernel(const bf16* __rest
         const float inv = 1.f / l;
         bf16* orow = out + ((size_t)b * N + r) * heads * D + (size_t)hd * D;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < D / 8; ++i)
           *reinterpret_cast<uint32_t*>(orow + i * 8 + 2 * q) = pack_bf16(o[i][2 * h] * inv, o[i][2 * h + 1] * inv);
         if (q == 0) lse[((size_t)b * heads + hd) * N + r] = m_run[h] * scale + logf(l);
       }
@@ -194,6 +206,7 @@ __global__ void __launch_bounds__(256, 3) mhsa_fwd_mma_kernel(const bf16* __rest
 }
 
 // D[i] = sum_c dO[i][c] * O[i][c]
+template <int D>
 __global__ void __launch_bounds__(256) mhsa_rowdot_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout,
                                                           float* __restrict__ drow, int B, int N, int heads) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b, n, head)
@@ -207,7 +220,7 @@ __global__ void __launch_bounds__(256) mhsa_rowdot_kernel(const bf16* __restrict
   const uint4* pg = reinterpret_cast<const uint4*>(dout + (size_t)idx * D);
   float acc = 0.f;
 #pragma unroll
-  for (int v4 = 0; v4 < 4; ++v4) {
+  for (int v4 = 0; v4 < D / 8; ++v4) {
     const uint4 a = po[v4], g = pg[v4];
     const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
     const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&g);
@@ -222,10 +235,13 @@ __global__ void __launch_bounds__(256) mhsa_rowdot_kernel(const bf16* __restrict
 }
 
 // dQ: warp per 16 queries; S = Q K^T, P = exp(S*scale - lse), dP = dO V^T, dS = P*(dP - D), dQ = scale * dS K
-__global__ void __launch_bounds__(256, 3) mhsa_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+template <int D>
+__global__ void __launch_bounds__(256, (D == 32 ? 3 : 1)) mhsa_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                               const float* __restrict__ lse, const float* __restrict__ drow,
                                                               bf16* __restrict__ dqkv, int N, int heads, float scale,
                                                               int rows_pad) {
+  constexpr int ROWP = D + 8;
+  constexpr uint32_t ROWB = ROWP * 2;
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* sK = reinterpret_cast<bf16*>(smraw);
   bf16* sV = sK + (size_t)rows_pad * ROWP;
@@ -233,19 +249,19 @@ __global__ void __launch_bounds__(256, 3) mhsa_bwd_dq_mma_kernel(const bf16* __r
   const size_t tok = (size_t)3 * heads * D, otok = (size_t)heads * D;
   const bf16* qb = qkv + (size_t)b * N * tok + (size_t)hd * D;
   const bf16* gb = dout + (size_t)b * N * otok + (size_t)hd * D;
-  stage_rows(sK, qb + heads * D, tok, N, rows_pad);
-  stage_rows(sV, qb + 2 * heads * D, tok, N, rows_pad);
+  stage_rows<D>(sK, qb + heads * D, tok, N, rows_pad);
+  stage_rows<D>(sV, qb + 2 * heads * D, tok, N, rows_pad);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int gi = lane >> 2, q = lane & 3;
   const float sl2 = scale * 1.4426950408889634f;
   const float* L = lse + ((size_t)b * heads + hd) * N;
   const float* Dr = drow + ((size_t)b * heads + hd) * N;
-  const uint32_t sK_T = smem_u32(sK) + lane_offT(lane), sV_T = smem_u32(sV) + lane_offT(lane), sK_R = smem_u32(sK) + lane_offR(lane);
+  const uint32_t sK_T = smem_u32(sK) + lane_offT<D>(lane), sV_T = smem_u32(sV) + lane_offT<D>(lane), sK_R = smem_u32(sK) + lane_offR<D>(lane);
   for (int row0 = warp * 16; row0 < N; row0 += nwarp * 16) {
-    uint32_t qa[2][4], ga[2][4];
-    load_a_rows(qa, qb, tok, row0, N, lane);
-    load_a_rows(ga, gb, otok, row0, N, lane);
+    uint32_t qa[D / 16][4], ga[D / 16][4];
+    load_a_rows<D>(qa, qb, tok, row0, N, lane);
+    load_a_rows<D>(ga, gb, otok, row0, N, lane);
     float l2[2], dr[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -253,9 +269,9 @@ __global__ void __launch_bounds__(256, 3) mhsa_bwd_dq_mma_kernel(const bf16* __r
       l2[h] = (r < N) ? L[r] * 1.4426950408889634f : 0.f;
       dr[h] = (r < N) ? Dr[r] : 0.f;
     }
-    float dq[4][4];
+    float dq[D / 8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < D / 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
     for (int k0 = 0; k0 < N; k0 += 16) {
@@ -264,8 +280,8 @@ __global__ void __launch_bounds__(256, 3) mhsa_bwd_dq_mma_kernel(const bf16* __r
       for (int nb = 0; nb < 2; ++nb) {
         s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
         dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
-        mma_rowsT(s[nb], qa, sK_T + (uint32_t)(k0 + nb * 8) * ROWB);
-        mma_rowsT(dp[nb], ga, sV_T + (uint32_t)(k0 + nb * 8) * ROWB);
+        mma_rowsT<D>(s[nb], qa, sK_T + (uint32_t)(k0 + nb * 8) * ROWB);
+        mma_rowsT<D>(dp[nb], ga, sV_T + (uint32_t)(k0 + nb * 8) * ROWB);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int key = k0 + nb * 8 + 2 * q + (j & 1);
@@ -275,7 +291,7 @@ __global__ void __launch_bounds__(256, 3) mhsa_bwd_dq_mma_kernel(const bf16* __r
       }
       uint32_t pa[4] = {pack_bf16(s[0][0], s[0][1]), pack_bf16(s[0][2], s[0][3]), pack_bf16(s[1][0], s[1][1]),
                         pack_bf16(s[1][2], s[1][3])};
-      mma_rows(dq, pa, sK_R + (uint32_t)k0 * ROWB);
+      mma_rows<D>(dq, pa, sK_R + (uint32_t)k0 * ROWB);
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -283,7 +299,7 @@ __global__ void __launch_bounds__(256, 3) mhsa_bwd_dq_mma_kernel(const bf16* __r
       if (r < N) {
         bf16* drowp = dqkv + ((size_t)b * N + r) * tok + (size_t)hd * D;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < D / 8; ++i)
           *reinterpret_cast<uint32_t*>(drowp + i * 8 + 2 * q) = pack_bf16(dq[i][2 * h] * scale, dq[i][2 * h + 1] * scale);
       }
     }
@@ -292,10 +308,13 @@ __global__ void __launch_bounds__(256, 3) mhsa_bwd_dq_mma_kernel(const bf16* __r
 
 // dK, dV: warp per 16 keys; S^T = K Q^T, P^T = exp(S^T*scale - lse[query]), dV = P^T dO, dP^T = V dO^T,
 // dS^T = P^T*(dP^T - D[query]), dK = scale * dS^T Q.   Q, dO, lse, D of the (b, head) in smem.
-__global__ void __launch_bounds__(256) mhsa_bwd_dkv_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+template <int D>
+__global__ void __launch_bounds__(256, (D == 32 ? 2 : 1)) mhsa_bwd_dkv_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                                const float* __restrict__ lse,
                                                                const float* __restrict__ drow, bf16* __restrict__ dqkv,
                                                                int N, int heads, float scale, int rows_pad) {
+  constexpr int ROWP = D + 8;
+  constexpr uint32_t ROWB = ROWP * 2;
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* sQ = reinterpret_cast<bf16*>(smraw);
   bf16* sG = sQ + (size_t)rows_pad * ROWP;
@@ -305,8 +324,8 @@ __global__ void __launch_bounds__(256) mhsa_bwd_dkv_mma_kernel(const bf16* __res
   const size_t tok = (size_t)3 * heads * D, otok = (size_t)heads * D;
   const bf16* qb = qkv + (size_t)b * N * tok + (size_t)hd * D;
   const bf16* gb = dout + (size_t)b * N * otok + (size_t)hd * D;
-  stage_rows(sQ, qb, tok, N, rows_pad);
-  stage_rows(sG, gb, otok, N, rows_pad);
+  stage_rows<D>(sQ, qb, tok, N, rows_pad);
+  stage_rows<D>(sG, gb, otok, N, rows_pad);
   for (int n = threadIdx.x; n < rows_pad; n += blockDim.x) {
     sL[n] = (n < N) ? lse[((size_t)b * heads + hd) * N + n] * 1.4426950408889634f : 0.f;
     sD[n] = (n < N) ? drow[((size_t)b * heads + hd) * N + n] : 0.f;
@@ -315,15 +334,15 @@ __global__ void __launch_bounds__(256) mhsa_bwd_dkv_mma_kernel(const bf16* __res
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int gi = lane >> 2, q = lane & 3;
   const float sl2 = scale * 1.4426950408889634f;
-  const uint32_t sQ_T = smem_u32(sQ) + lane_offT(lane), sG_T = smem_u32(sG) + lane_offT(lane);
-  const uint32_t sQ_R = smem_u32(sQ) + lane_offR(lane), sG_R = smem_u32(sG) + lane_offR(lane);
+  const uint32_t sQ_T = smem_u32(sQ) + lane_offT<D>(lane), sG_T = smem_u32(sG) + lane_offT<D>(lane);
+  const uint32_t sQ_R = smem_u32(sQ) + lane_offR<D>(lane), sG_R = smem_u32(sG) + lane_offR<D>(lane);
   for (int key0 = warp * 16; key0 < N; key0 += nwarp * 16) {
-    uint32_t ka[2][4], va[2][4];
-    load_a_rows(ka, qb + heads * D, tok, key0, N, lane);
-    load_a_rows(va, qb + 2 * heads * D, tok, key0, N, lane);
-    float dk[4][4], dv[4][4];
+    uint32_t ka[D / 16][4], va[D / 16][4];
+    load_a_rows<D>(ka, qb + heads * D, tok, key0, N, lane);
+    load_a_rows<D>(va, qb + 2 * heads * D, tok, key0, N, lane);
+    float dk[D / 8][4], dv[D / 8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < D / 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) { dk[i][j] = 0.f; dv[i][j] = 0.f; }
     for (int i0 = 0; i0 < N; i0 += 16) {
@@ -333,8 +352,8 @@ __global__ void __launch_bounds__(256) mhsa_bwd_dkv_mma_kernel(const bf16* __res
       for (int nb = 0; nb < 2; ++nb) {
         s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
         dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
-        mma_rowsT(s[nb], ka, sQ_T + (uint32_t)(i0 + nb * 8) * ROWB);     // S^T[key][query]
-        mma_rowsT(dp[nb], va, sG_T + (uint32_t)(i0 + nb * 8) * ROWB);    // dP^T[key][query]
+        mma_rowsT<D>(s[nb], ka, sQ_T + (uint32_t)(i0 + nb * 8) * ROWB);     // S^T[key][query]
+        mma_rowsT<D>(dp[nb], va, sG_T + (uint32_t)(i0 + nb * 8) * ROWB);    // dP^T[key][query]
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int qi = i0 + nb * 8 + 2 * q + (j & 1);
@@ -347,8 +366,8 @@ __global__ void __launch_bounds__(256) mhsa_bwd_dkv_mma_kernel(const bf16* __res
         ds[nb * 2 + 0] = pack_bf16(dp[nb][0], dp[nb][1]);
         ds[nb * 2 + 1] = pack_bf16(dp[nb][2], dp[nb][3]);
       }
-      mma_rows(dv, pp, sG_R + (uint32_t)i0 * ROWB);
-      mma_rows(dk, ds, sQ_R + (uint32_t)i0 * ROWB);
+      mma_rows<D>(dv, pp, sG_R + (uint32_t)i0 * ROWB);
+      mma_rows<D>(dk, ds, sQ_R + (uint32_t)i0 * ROWB);
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -357,7 +376,7 @@ __global__ void __launch_bounds__(256) mhsa_bwd_dkv_mma_kernel(const bf16* __res
         bf16* kp = dqkv + ((size_t)b * N + r) * tok + (size_t)heads * D + (size_t)hd * D;
         bf16* vp = kp + (size_t)heads * D;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < D / 8; ++i) {
           *reinterpret_cast<uint32_t*>(kp + i * 8 + 2 * q) = pack_bf16(dk[i][2 * h] * scale, dk[i][2 * h + 1] * scale);
           *reinterpret_cast<uint32_t*>(vp + i * 8 + 2 * q) = pack_bf16(dv[i][2 * h], dv[i][2 * h + 1]);
         }
@@ -374,33 +393,51 @@ int pick_warps(int N) {
 
 }  // namespace
 
-int apb_mhsa_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, int heads, float scale, cudaStream_t st) {
+template <int D>
+static int mhsa_fwd_mma_t(const void* qkv, void* out, float* lse, int B, int N, int heads, float scale, cudaStream_t st) {
+  constexpr int ROWP = D + 8;
   const int rows_pad = (N + 63) / 64 * 64;
   const size_t smem = (size_t)2 * rows_pad * ROWP * sizeof(bf16);
   APB_CHECK_ARG(smem <= 227 * 1024, APB_ERR_UNSUPPORTED, "mhsa_fwd_mma: N=%d needs %zu B smem", N, smem);
-  cudaFuncSetAttribute(mhsa_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  mhsa_fwd_mma_kernel<<<B * heads, pick_warps(N) * 32, smem, st>>>((const bf16*)qkv, (bf16*)out, lse, N, heads, scale, rows_pad);
+  cudaFuncSetAttribute(mhsa_fwd_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mhsa_fwd_mma_kernel<D><<<B * heads, pick_warps(N) * 32, smem, st>>>((const bf16*)qkv, (bf16*)out, lse, N, heads, scale, rows_pad);
   APB_LAUNCH_CHECK("mhsa_fwd_mma");
   return 0;
 }
 
-int apb_mhsa_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
-                     int B, int N, int heads, float scale, cudaStream_t st) {
+template <int D>
+static int mhsa_bwd_mma_t(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
+                          int B, int N, int heads, float scale, cudaStream_t st) {
+  constexpr int ROWP = D + 8;
   const int rows_pad = (N + 15) / 16 * 16;
   const size_t smem1 = (size_t)2 * rows_pad * ROWP * sizeof(bf16);
   const size_t smem2 = smem1 + (size_t)2 * rows_pad * sizeof(float);
   APB_CHECK_ARG(smem2 <= 227 * 1024, APB_ERR_UNSUPPORTED, "mhsa_bwd_mma: N=%d needs %zu B smem", N, smem2);
   const long long total = (long long)B * N * heads;
-  mhsa_rowdot_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, workspace, B, N, heads);
+  mhsa_rowdot_kernel<D><<<ceil_div(total, 256), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, workspace, B, N, heads);
   APB_LAUNCH_CHECK("mhsa_rowdot");
-  cudaFuncSetAttribute(mhsa_bwd_dq_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-  cudaFuncSetAttribute(mhsa_bwd_dkv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+  cudaFuncSetAttribute(mhsa_bwd_dq_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+  cudaFuncSetAttribute(mhsa_bwd_dkv_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
   const int threads = pick_warps(N) * 32;
-  mhsa_bwd_dq_mma_kernel<<<B * heads, threads, smem1, st>>>((const bf16*)qkv, (const bf16*)dout, lse, workspace, (bf16*)dqkv, N,
-                                                           heads, scale, rows_pad);
+  mhsa_bwd_dq_mma_kernel<D><<<B * heads, threads, smem1, st>>>((const bf16*)qkv, (const bf16*)dout, lse, workspace, (bf16*)dqkv,
+                                                              N, heads, scale, rows_pad);
   APB_LAUNCH_CHECK("mhsa_bwd_dq_mma");
-  mhsa_bwd_dkv_mma_kernel<<<B * heads, threads, smem2, st>>>((const bf16*)qkv, (const bf16*)dout, lse, workspace, (bf16*)dqkv,
-                                                            N, heads, scale, rows_pad);
+  mhsa_bwd_dkv_mma_kernel<D><<<B * heads, threads, smem2, st>>>((const bf16*)qkv, (const bf16*)dout, lse, workspace, (bf16*)dqkv,
+                                                               N, heads, scale, rows_pad);
   APB_LAUNCH_CHECK("mhsa_bwd_dkv_mma");
   return 0;
+}
+
+// D = 32 or 64; anything else -> APB_ERR_UNSUPPORTED (the dispatcher then uses the SIMT kernels)
+int apb_mhsa_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, cudaStream_t st) {
+  if (D == 32) return mhsa_fwd_mma_t<32>(qkv, out, lse, B, N, heads, scale, st);
+  if (D == 64) return mhsa_fwd_mma_t<64>(qkv, out, lse, B, N, heads, scale, st);
+  return APB_ERR_UNSUPPORTED;
+}
+
+int apb_mhsa_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
+                     int B, int N, int heads, int D, float scale, cudaStream_t st) {
+  if (D == 32) return mhsa_bwd_mma_t<32>(qkv, out, dout, lse, dqkv, workspace, B, N, heads, scale, st);
+  if (D == 64) return mhsa_bwd_mma_t<64>(qkv, out, dout, lse, dqkv, workspace, B, N, heads, scale, st);
+  return APB_ERR_UNSUPPORTED;
 }

@@ -27,21 +27,25 @@ int apb_outlook_bwd(const void* v, const void* logits, const void* dy, void* dv,
   return apb_outlook_bwd_simt(v, logits, dy, dv, dlogits, B, H, W, heads, scale, lpitch, dtype, stream);
 }
 
-int apb_mhsa_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, int heads, float scale, cudaStream_t st);
+int apb_mhsa_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, cudaStream_t st);
 int apb_mhsa_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
-                     int B, int N, int heads, float scale, cudaStream_t st);
+                     int B, int N, int heads, int D, float scale, cudaStream_t st);
 
-// bf16 + head_dim 32 (every VOLO variant) -> tensor-core kernels; anything else -> CUDA-core fp32 kernels
+// bf16 + head_dim 32 (every VOLO variant) or 64 (DeiT) -> tensor-core kernels; anything else -> CUDA-core fp32 kernels
 int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, int dtype,
                  apb_stream_t stream) {
-  if (dtype == APB_BF16 && D == 32 && B > 0 && N > 0 && heads > 0)
-    return apb_mhsa_fwd_mma(qkv, out, lse, B, N, heads, scale, APB_STREAM(stream));
+  if (dtype == APB_BF16 && (D == 32 || D == 64) && B > 0 && N > 0 && heads > 0) {
+    const int rc = apb_mhsa_fwd_mma(qkv, out, lse, B, N, heads, D, scale, APB_STREAM(stream));
+    if (rc != APB_ERR_UNSUPPORTED) return rc;
+  }
   return apb_mhsa_fwd_simt(qkv, out, lse, B, N, heads, D, scale, dtype, stream);
 }
 
 int apb_mhsa_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
                  int B, int N, int heads, int D, float scale, int dtype, apb_stream_t stream) {
-  if (dtype == APB_BF16 && D == 32 && B > 0 && N > 0 && heads > 0)
-    return apb_mhsa_bwd_mma(qkv, out, dout, lse, dqkv, workspace, B, N, heads, scale, APB_STREAM(stream));
+  if (dtype == APB_BF16 && (D == 32 || D == 64) && B > 0 && N > 0 && heads > 0) {
+    const int rc = apb_mhsa_bwd_mma(qkv, out, dout, lse, dqkv, workspace, B, N, heads, D, scale, APB_STREAM(stream));
+    if (rc != APB_ERR_UNSUPPORTED) return rc;
+  }
   return apb_mhsa_bwd_simt(qkv, out, dout, lse, dqkv, workspace, B, N, heads, D, scale, dtype, stream);
 }

@@ -2,8 +2,10 @@
 //
 //   reference: nn.Unfold(3,1,2) -> softmax(scale*logits) -> attn @ v -> F.fold          (models/volo.py:83-98)
 //
-// A CTA owns a band of TR window rows of one image (all window columns, all heads).  It stages the (2TR+3)-row pixel
-// band of v (and dy in the backward) ONCE in shared memory with coalesced 16-byte loads; every (window, head) unit
+// A CTA owns a band of TR window rows x TC window columns of one image (all heads; TC = all columns whenever that fits
+// shared memory -- every 224-px VOLO stage -- else the grid is also tiled along x, e.g. the 48x48 grids of volo_d2@384).
+// It stages the (2TR+3) x (2TC+3) pixel band of v (and dy in the backward) ONCE in shared memory with coalesced 16-byte
+// loads; every (window, head) unit
 // then is a 16x16x16 mma.sync problem whose operands come straight from that tile:
 //   forward : out[P][c]  = sum_Q A[P][Q] v[pix(Q)][c]        A = softmax fragment built in registers (warp shuffles)
 //   backward: dA[P][Q]   = <dy[pix(P)], v[pix(Q)]>           ; dlogits = scale * A o (dA - rowsum(A o dA))
@@ -63,15 +65,16 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 struct Geo {
   int B, H, W, heads, h, w, lpitch;
-  int TR;              // window rows owned per CTA
-  int nWR;             // window rows computed per CTA (TR + 1 halo)
+  int TR, TC;          // window rows / columns owned per CTA
+  int nWR, nWC;        // window rows / columns computed per CTA (+1 halo on the far side when the axis is tiled)
+  int nCB;             // CTAs along x
   int PR, PC, Cp;      // staged pixel rows / cols, padded channel pitch (bf16 elements)
   float scale;
 };
 
-// stage pixel rows [y0, y0+PR) x cols [-1, -1+PC) of src[b] (NHWC bf16) into s[PR][PC][Cp]; outside the image -> zeros
+// stage pixel rows [y0, y0+PR) x cols [x0, x0+PC) of src[b] (NHWC bf16) into s[PR][PC][Cp]; outside the image -> zeros
 template <int NT>
-__device__ __forceinline__ void stage_band(bf16* s, const bf16* __restrict__ src, const Geo& g, int b, int y0) {
+__device__ __forceinline__ void stage_band(bf16* s, const bf16* __restrict__ src, const Geo& g, int b, int y0, int x0) {
   const int C = g.heads * HD;
   const int cpr = C >> 3;                                  // 16-byte chunks per pixel
   const int per_row = g.PC * cpr;
@@ -79,12 +82,12 @@ __device__ __forceinline__ void stage_band(bf16* s, const bf16* __restrict__ src
   for (int py = 0; py < g.PR; ++py) {
     const int y = y0 + py;
     const bool yok = (y >= 0 && y < g.H);
-    const bf16* grow = img + (size_t)(yok ? y : 0) * g.W * C - C;   // column x = px - 1
+    const bf16* grow = img + ((ptrdiff_t)(yok ? y : 0) * g.W + x0) * C;   // column x = x0 + px
     bf16* srow = s + (size_t)py * g.PC * g.Cp;
     for (int e = threadIdx.x; e < per_row; e += NT) {
       const int px = e / cpr, ch = e - px * cpr;
       uint4 val = make_uint4(0u, 0u, 0u, 0u);
-      if (yok && px >= 1 && px <= g.W) val = *reinterpret_cast<const uint4*>(grow + (size_t)px * C + ch * 8);
+      if (yok && x0 + px >= 0 && x0 + px < g.W) val = *reinterpret_cast<const uint4*>(grow + (ptrdiff_t)px * C + ch * 8);
       *reinterpret_cast<uint4*>(srow + px * g.Cp + ch * 8) = val;
     }
   }
@@ -179,8 +182,8 @@ __device__ __forceinline__ void stage_unit(uint32_t blk, const float (&acc)[4][4
 
 // fold as a gather: output pixel (ly, lx) of the band (local coords) sums its covering (window, row) staging entries
 template <int NT>
-__device__ __forceinline__ void gather_store(uint32_t sOut_s, bf16* __restrict__ dst_band, const Geo& g, int rows, int nWR_eff,
-                                             int hd, int ly0, int lx0) {
+__device__ __forceinline__ void gather_store(uint32_t sOut_s, bf16* __restrict__ dst_band, const Geo& g, int rows, int cols,
+                                             int nWR_eff, int wb, int hd, int ly0, int lx0) {
   const int C = g.heads * HD;
   const int c4 = (threadIdx.x & 7) * 4;
   constexpr int S = NT / 8;                                // pixels handled per sweep
@@ -190,8 +193,8 @@ __device__ __forceinline__ void gather_store(uint32_t sOut_s, bf16* __restrict__
     // rows: even -> (lr = ly/2, ki = 1); odd -> (lr = (ly-1)/2, ki = 2) and (lr = (ly+1)/2, ki = 0); same for columns
     const int lr0 = ly >> 1, lc0 = lx >> 1;
     const int ki0 = (ly & 1) ? 2 : 1, kj0 = (lx & 1) ? 2 : 1;
-    const bool r2 = (ly & 1) && (lr0 + 1 < nWR_eff), c2 = (lx & 1) && (lc0 + 1 < g.w);
-    const uint32_t e00 = sOut_s + (uint32_t)((((lr0 * g.w + lc0) * 9 + ki0 * 3 + kj0) * OS + c4) * 4);
+    const bool r2 = (ly & 1) && (lr0 + 1 < nWR_eff), c2 = (lx & 1) && (lc0 + 1 < wb);
+    const uint32_t e00 = sOut_s + (uint32_t)((((lr0 * wb + lc0) * 9 + ki0 * 3 + kj0) * OS + c4) * 4);
     {
       const float4 t = lds128(e00);
       s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
@@ -201,7 +204,7 @@ __device__ __forceinline__ void gather_store(uint32_t sOut_s, bf16* __restrict__
       s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
     }
     if (r2) {   // window (lr0+1, lc0), ki = 0
-      const uint32_t e10 = e00 + (uint32_t)((g.w * 9 - ki0 * 3) * OS * 4);
+      const uint32_t e10 = e00 + (uint32_t)((wb * 9 - ki0 * 3) * OS * 4);
       const float4 t = lds128(e10);
       s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
       if (c2) {
@@ -214,7 +217,7 @@ __device__ __forceinline__ void gather_store(uint32_t sOut_s, bf16* __restrict__
     pk.y = pack_bf16(s.z, s.w);
     *reinterpret_cast<uint2*>(dst_band + ((size_t)ly * g.W + lx) * C + hd * HD + c4) = pk;
     lx += S;
-    while (lx >= g.W) { lx -= g.W; ++ly; }
+    while (lx >= cols) { lx -= cols; ++ly; }
   }
 }
 
@@ -226,33 +229,38 @@ __global__ void __launch_bounds__(NT, 1) outlook_fwd_mma_kernel(const bf16* __re
   bf16* sV = zero + 32;
   const uint32_t tile_bytes = (uint32_t)(g.PR * g.PC * g.Cp * 2);
   const uint32_t zero_s = smem_u32(zero), sV_s = zero_s + 64, sOut_s = sV_s + tile_bytes;
-  const int b = blockIdx.y, i0 = blockIdx.x * g.TR;
+  const int b = blockIdx.y, bi = blockIdx.x / g.nCB, bj = blockIdx.x - bi * g.nCB;
+  const int i0 = bi * g.TR, j0 = bj * g.TC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int nwarp = NT / 32;
   const int gi = lane >> 2, q = lane & 3;
   if (threadIdx.x < 32) zero[threadIdx.x] = __float2bfloat16_rn(0.f);
-  stage_band<NT>(sV, v, g, b, 2 * i0 - 1);
+  stage_band<NT>(sV, v, g, b, 2 * i0 - 1, 2 * j0 - 1);
   const int nWR = min(g.nWR, g.h - i0);
-  const int units = nWR * g.w;
+  const int wb = min(g.nWC, g.w - j0);
+  const int units = nWR * wb;
   const LaneGeo L = lane_geo(g, lane);
   const float sl2 = g.scale * 1.4426950408889634f;
-  const int rows = min(2 * g.TR, g.H - 2 * i0);
+  const int rows = min(2 * g.TR, g.H - 2 * i0), cols = min(2 * g.TC, g.W - 2 * j0);
   const int ps = threadIdx.x >> 3;
-  const int ly0 = ps / g.W, lx0 = ps - ly0 * g.W;
-  bf16* ydst = y + ((size_t)b * g.H + 2 * i0) * g.W * (g.heads * HD);
+  const int ly0 = ps / cols, lx0 = ps - ly0 * cols;
+  bf16* ydst = y + (((size_t)b * g.H + 2 * i0) * g.W + 2 * j0) * (g.heads * HD);
   const uint32_t row_pitch = (uint32_t)(g.PC * g.Cp * 2);
   // logits of a warp's NEXT unit are fetched while the current one is computed (the only global loads in the loop)
-  const bf16* lbase = logits + ((size_t)b * g.h + i0) * g.w * g.lpitch;
-  RawLogits nxt = load_logits(lbase + (size_t)(warp < units ? warp : 0) * g.lpitch, gi, q);
+  const bf16* lbase = logits + (((size_t)b * g.h + i0) * g.w + j0) * g.lpitch;
+  const int lr_f = warp / wb, lc_f = warp - lr_f * wb;           // this warp's first unit of every head
+  RawLogits nxt = load_logits(lbase + (size_t)(warp < units ? lr_f * g.w + lc_f : 0) * g.lpitch, gi, q);
   __syncthreads();
   for (int hd = 0; hd < g.heads; ++hd) {
-    int lr = warp / g.w, lc = warp - lr * g.w;
+    int lr = lr_f, lc = lc_f;
     for (int u = warp; u < units; u += nwarp) {
       const RawLogits cur = nxt;
+      int nlr = lr, nlc = lc + nwarp;
+      while (nlc >= wb) { nlc -= wb; ++nlr; }
       {
-        int nu = u + nwarp, nh = hd;
-        if (nu >= units) { nu = warp; ++nh; }
-        if (nh < g.heads && nu < units) nxt = load_logits(lbase + (size_t)nu * g.lpitch + nh * 81, gi, q);
+        int plr = nlr, plc = nlc, nh = hd;
+        if (u + nwarp >= units) { plr = lr_f; plc = lc_f; ++nh; }
+        if (nh < g.heads) nxt = load_logits(lbase + (size_t)(plr * g.w + plc) * g.lpitch + nh * 81, gi, q);
       }
       float pf[2][4];
       softmax_frag(cur, sl2, gi, q, pf);
@@ -264,11 +272,11 @@ __global__ void __launch_bounds__(NT, 1) outlook_fwd_mma_kernel(const bf16* __re
       const uint32_t ub = sV_s + (uint32_t)(2 * lr) * row_pitch + (uint32_t)((2 * lc * g.Cp + hd * HD) * 2);
       mma_rows(acc, a, ub, zero_s, L);
       stage_unit(sOut_s + (uint32_t)(u * 9 * OS * 4), acc, L, gi);
-      lc += nwarp;
-      while (lc >= g.w) { lc -= g.w; ++lr; }
+      lr = nlr;
+      lc = nlc;
     }
     __syncthreads();
-    gather_store<NT>(sOut_s, ydst, g, rows, nWR, hd, ly0, lx0);
+    gather_store<NT>(sOut_s, ydst, g, rows, cols, nWR, wb, hd, ly0, lx0);
     __syncthreads();
   }
 }
@@ -283,36 +291,41 @@ __global__ void __launch_bounds__(NT, 1) outlook_bwd_mma_kernel(const bf16* __re
   const uint32_t tile_bytes = (uint32_t)(g.PR * g.PC * g.Cp * 2);
   bf16* sG = sV + (size_t)g.PR * g.PC * g.Cp;
   const uint32_t zero_s = smem_u32(zero), sV_s = zero_s + 64, sG_s = sV_s + tile_bytes, sOut_s = sG_s + tile_bytes;
-  const int b = blockIdx.y, i0 = blockIdx.x * g.TR;
+  const int b = blockIdx.y, bi = blockIdx.x / g.nCB, bj = blockIdx.x - bi * g.nCB;
+  const int i0 = bi * g.TR, j0 = bj * g.TC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int nwarp = NT / 32;
   const int gi = lane >> 2, q = lane & 3;
   if (threadIdx.x < 32) zero[threadIdx.x] = __float2bfloat16_rn(0.f);
-  stage_band<NT>(sV, v, g, b, 2 * i0 - 1);
-  stage_band<NT>(sG, dy, g, b, 2 * i0 - 1);
+  stage_band<NT>(sV, v, g, b, 2 * i0 - 1, 2 * j0 - 1);
+  stage_band<NT>(sG, dy, g, b, 2 * i0 - 1, 2 * j0 - 1);
   const int nWR = min(g.nWR, g.h - i0);
-  const int units = nWR * g.w;
+  const int wb = min(g.nWC, g.w - j0);
+  const int units = nWR * wb;
   const LaneGeo L = lane_geo(g, lane);
   const float sl2 = g.scale * 1.4426950408889634f;
-  const int rows = min(2 * g.TR, g.H - 2 * i0);
+  const int rows = min(2 * g.TR, g.H - 2 * i0), cols = min(2 * g.TC, g.W - 2 * j0);
   const int ps = threadIdx.x >> 3;
-  const int ly0 = ps / g.W, lx0 = ps - ly0 * g.W;
-  bf16* ddst = dv + ((size_t)b * g.H + 2 * i0) * g.W * (g.heads * HD);
+  const int ly0 = ps / cols, lx0 = ps - ly0 * cols;
+  bf16* ddst = dv + (((size_t)b * g.H + 2 * i0) * g.W + 2 * j0) * (g.heads * HD);
   const uint32_t row_pitch = (uint32_t)(g.PC * g.Cp * 2);
   const int npad = g.lpitch - g.heads * 81;
-  const size_t lband = ((size_t)b * g.h + i0) * g.w * g.lpitch;
+  const size_t lband = (((size_t)b * g.h + i0) * g.w + j0) * g.lpitch;
   const bf16* lbase = logits + lband;
   bf16* dlbase = dlogits + lband;
-  RawLogits nxt = load_logits(lbase + (size_t)(warp < units ? warp : 0) * g.lpitch, gi, q);
+  const int lr_f = warp / wb, lc_f = warp - lr_f * wb;
+  RawLogits nxt = load_logits(lbase + (size_t)(warp < units ? lr_f * g.w + lc_f : 0) * g.lpitch, gi, q);
   __syncthreads();
   for (int hd = 0; hd < g.heads; ++hd) {
-    int lr = warp / g.w, lc = warp - lr * g.w;
+    int lr = lr_f, lc = lc_f;
     for (int u = warp; u < units; u += nwarp) {
       const RawLogits cur = nxt;
+      int nlr = lr, nlc = lc + nwarp;
+      while (nlc >= wb) { nlc -= wb; ++nlr; }
       {
-        int nu = u + nwarp, nh = hd;
-        if (nu >= units) { nu = warp; ++nh; }
-        if (nh < g.heads && nu < units) nxt = load_logits(lbase + (size_t)nu * g.lpitch + nh * 81, gi, q);
+        int plr = nlr, plc = nlc, nh = hd;
+        if (u + nwarp >= units) { plr = lr_f; plc = lc_f; ++nh; }
+        if (nh < g.heads) nxt = load_logits(lbase + (size_t)(plr * g.w + plc) * g.lpitch + nh * 81, gi, q);
       }
       float pf[2][4];
       softmax_frag(cur, sl2, gi, q, pf);
@@ -333,13 +346,14 @@ __global__ void __launch_bounds__(NT, 1) outlook_bwd_mma_kernel(const bf16* __re
           mma16816(da[nb], a1, bq[2], bq[3]);
         }
       }
-      // ---- dlogits = scale * A o (dA - sum_Q A o dA)   (own rows only: the halo row belongs to the next band)
+      // ---- dlogits = scale * A o (dA - sum_Q A o dA)   (own windows only: halo windows belong to the neighbouring CTA)
       float r0 = pf[0][0] * da[0][0] + pf[0][1] * da[0][1] + pf[1][0] * da[1][0];
       float r1 = pf[0][2] * da[0][2] + pf[0][3] * da[0][3] + pf[1][2] * da[1][2];
       r0 = quad_sum(r0);
       r1 = quad_sum(r1);
-      if (lr < g.TR) {
-        bf16* dl = dlbase + (size_t)u * g.lpitch + hd * 81;
+      if (lr < g.TR && lc < g.TC) {
+        const size_t lu = (size_t)(lr * g.w + lc) * g.lpitch;
+        bf16* dl = dlbase + lu + hd * 81;
         bf16* drow = dl + gi * 9 + 2 * q;
         drow[0] = __float2bfloat16_rn(g.scale * pf[0][0] * (da[0][0] - r0));
         drow[1] = __float2bfloat16_rn(g.scale * pf[0][1] * (da[0][1] - r0));
@@ -350,7 +364,7 @@ __global__ void __launch_bounds__(NT, 1) outlook_bwd_mma_kernel(const bf16* __re
           if (q == 0) dl[80] = __float2bfloat16_rn(g.scale * pf[1][2] * (da[1][2] - r1));
         }
         if (hd == 0 && lane >= 9 && lane - 9 < npad)
-          dlbase[(size_t)u * g.lpitch + g.heads * 81 + (lane - 9)] = __float2bfloat16_rn(0.f);   // TMA padding columns
+          dlbase[lu + g.heads * 81 + (lane - 9)] = __float2bfloat16_rn(0.f);   // TMA padding columns
       }
       // ---- dvw[Q][c] = sum_P A[P][Q] dy[pix P][c] : A operand = A^T (movmatrix), B operand = dy rows (ldmatrix.trans)
       const uint32_t at[4] = {movmatrix_t(pack_bf16(pf[0][0], pf[0][1])), movmatrix_t(pack_bf16(pf[1][0], pf[1][1])),
@@ -360,28 +374,44 @@ __global__ void __launch_bounds__(NT, 1) outlook_bwd_mma_kernel(const bf16* __re
       for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
       mma_rows(acc, at, sG_s + uoff, zero_s, L);
       stage_unit(sOut_s + (uint32_t)(u * 9 * OS * 4), acc, L, gi);
-      lc += nwarp;
-      while (lc >= g.w) { lc -= g.w; ++lr; }
+      lr = nlr;
+      lc = nlc;
     }
     __syncthreads();
-    gather_store<NT>(sOut_s, ddst, g, rows, nWR, hd, ly0, lx0);
+    gather_store<NT>(sOut_s, ddst, g, rows, cols, nWR, wb, hd, ly0, lx0);
     __syncthreads();
   }
 }
 
+// Pick the (TR, TC) band with the least recomputation that fits shared memory.  A tiled axis recomputes one halo
+// window row / column per CTA: work factor (TR+1)/TR * (TC+1)/TC; an untiled x axis (TC = w) has no column halo.
 int plan(Geo& g, bool bwd, size_t& smem) {
   const int C = g.heads * HD;
   g.Cp = C + 8;
-  g.PC = 2 * g.w + 3;
-  for (int tr = 3; tr >= 1; --tr) {      // largest band that fits: the halo window row is recomputed ((TR+1)/TR work)
-    g.TR = tr;
-    g.nWR = tr + 1;
-    g.PR = 2 * tr + 3;
-    const size_t tile = (size_t)g.PR * g.PC * g.Cp * sizeof(bf16);
-    smem = 64 + tile * (bwd ? 2 : 1) + (size_t)g.nWR * g.w * 9 * OS * sizeof(float);
-    if (smem <= 220 * 1024) return 0;
+  float best = 1e30f;
+  int btr = 0, btc = 0;
+  for (int tr = 3; tr >= 1; --tr) {
+    for (int nsplit = 1; nsplit <= 8; ++nsplit) {
+      const int tc = ceil_div(g.w, nsplit);
+      const int nwc = (nsplit == 1) ? g.w : tc + 1;
+      const size_t tile = (size_t)(2 * tr + 3) * (2 * nwc + 1) * g.Cp * sizeof(bf16);
+      const size_t need = 64 + tile * (bwd ? 2 : 1) + (size_t)(tr + 1) * nwc * 9 * OS * sizeof(float);
+      if (need > 220 * 1024) continue;
+      const float cost = (float)(tr + 1) / tr * (float)nwc / tc;
+      if (cost < best - 1e-6f) { best = cost; btr = tr; btc = tc; }
+      break;                                  // more column splits at this TR only add halo work
+    }
   }
-  return APB_ERR_UNSUPPORTED;
+  if (btr == 0) return APB_ERR_UNSUPPORTED;
+  g.TR = btr;
+  g.nWR = btr + 1;
+  g.PR = 2 * btr + 3;
+  g.TC = btc;
+  g.nCB = ceil_div(g.w, btc);
+  g.nWC = (g.nCB == 1) ? g.w : btc + 1;
+  g.PC = 2 * g.nWC + 1;
+  smem = 64 + (size_t)g.PR * g.PC * g.Cp * sizeof(bf16) * (bwd ? 2 : 1) + (size_t)g.nWR * g.nWC * 9 * OS * sizeof(float);
+  return 0;
 }
 
 Geo make_geo(int B, int H, int W, int heads, float scale, int lpitch) {
@@ -399,7 +429,7 @@ int apb_outlook_fwd_mma(const void* v, const void* logits, void* y, int B, int H
   if (plan(g, false, smem) != 0) return APB_ERR_UNSUPPORTED;
   constexpr int NT = 1024;
   cudaFuncSetAttribute(outlook_fwd_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid(ceil_div(g.h, g.TR), B);
+  dim3 grid(ceil_div(g.h, g.TR) * g.nCB, B);
   outlook_fwd_mma_kernel<NT><<<grid, NT, smem, st>>>((const bf16*)v, (const bf16*)logits, (bf16*)y, g);
   APB_LAUNCH_CHECK("outlook_fwd_mma");
   return 0;
@@ -412,7 +442,7 @@ int apb_outlook_bwd_mma(const void* v, const void* logits, const void* dy, void*
   if (plan(g, true, smem) != 0) return APB_ERR_UNSUPPORTED;
   constexpr int NT = 640;
   cudaFuncSetAttribute(outlook_bwd_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid(ceil_div(g.h, g.TR), B);
+  dim3 grid(ceil_div(g.h, g.TR) * g.nCB, B);
   outlook_bwd_mma_kernel<NT><<<grid, NT, smem, st>>>((const bf16*)v, (const bf16*)logits, (const bf16*)dy, (bf16*)dv,
                                                     (bf16*)dlogits, g);
   APB_LAUNCH_CHECK("outlook_bwd_mma");

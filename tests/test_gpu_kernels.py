@@ -22,7 +22,9 @@ def q(t, dtype):
 @pytest.mark.parametrize('dtype', DT)
 @pytest.mark.parametrize('simt', [True, False])
 @pytest.mark.parametrize('shape', [(2, 8, 8, 2), (2, 9, 7, 3), (1, 15, 13, 1), (3, 28, 28, 6), (1, 5, 6, 2), (2, 1, 1, 1),
-                                   (1, 2, 3, 1)])
+                                   (1, 2, 3, 1),
+                                   # wide grids: the tensor-core kernel tiles the band along x as well (volo_d2..d5 @ 384+)
+                                   (2, 48, 48, 8), (1, 33, 47, 8), (1, 20, 95, 4), (1, 7, 129, 12)])
 def test_outlook_core(shape, dtype, simt):
     dev = need_gpu()
     B, H, W, heads = shape
