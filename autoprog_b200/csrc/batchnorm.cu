@@ -50,7 +50,32 @@ __global__ void __launch_bounds__(256) bn_colstats_kernel(const T* __restrict__ 
   if (MODE == 1 && active) { ld8(mean + c0, mu); ld8(invstd + c0, is); }
   const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + (long long)rows_per_cta);
   if (active) {
-    for (long long r = r0 + slot; r < r1; r += groups) {
+    // UNR rows in flight per thread (all loads issued before the first use): the kernel is a pure HBM stream
+    constexpr int UNR = (MODE == 0) ? 4 : 2;
+    long long r = r0 + slot;
+    for (; r + (long long)(UNR - 1) * groups < r1; r += (long long)UNR * groups) {
+      float xv[UNR][8], yv[UNR][8], gv[UNR][8];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const size_t o = (size_t)(r + (long long)u * groups) * C + c0;
+        ld8(x + o, xv[u]);
+        if (MODE == 1) { ld8(y + o, yv[u]); ld8(dy + o, gv[u]); }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (MODE == 0) {
+            a0[j] += xv[u][j];
+            a1[j] = fmaf(xv[u][j], xv[u][j], a1[j]);
+          } else {
+            const float g = yv[u][j] > 0.f ? gv[u][j] : 0.f;
+            a0[j] += g;
+            a1[j] = fmaf(g, (xv[u][j] - mu[j]) * is[j], a1[j]);
+          }
+        }
+    }
+    for (; r < r1; r += groups) {
       float xv[8];
       ld8(x + (size_t)r * C + c0, xv);
       if (MODE == 0) {

@@ -105,11 +105,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 
-// erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): cdf = Phi(x), pdf_e = exp(-x^2/2)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): cdf = Phi(x), e = exp(-x^2/2).  The epilogue is issue-bound on the
+// CUDA cores, so both transcendentals are single MUFU ops (rcp.approx / ex2.approx: 1-2 ulp, far inside the bf16 output).
 __device__ __forceinline__ void phi_fast(float x, float& cdf, float& e) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.f));
-  e = exp2f(-z * z * 1.4426950408889634f);
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.f));
+  e = ex2_approx(x * x * -0.72134752044448170368f);     // exp(-x^2 / 2)
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

@@ -127,25 +127,33 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TC* __restrict__ dy, 
   }
 }
 
-// out[c] (+)= sum_r part[r][c]   (fixed order -> deterministic).  block = 32 columns x 8 row phases;
+// out[c] (+)= sum_r part[r][c]   (fixed order -> deterministic).  block = 32 columns x 32 row phases (a few hundred
+// partial rows: the loads of a phase are independent, 4 in flight per thread);
 // blockIdx.y selects one of up to two (partials, output) pairs so dgamma and dbeta share a launch.
-__global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ part0, float* __restrict__ out0,
-                                                              const float* __restrict__ part1, float* __restrict__ out1,
-                                                              int nparts, int C, int accumulate) {
-  __shared__ float s[8][33];
+__global__ void __launch_bounds__(1024) colsum_partials_kernel(const float* __restrict__ part0, float* __restrict__ out0,
+                                                               const float* __restrict__ part1, float* __restrict__ out1,
+                                                               int nparts, int C, int accumulate) {
+  __shared__ float s[32][33];
   const float* part = blockIdx.y == 0 ? part0 : part1;
   float* out = blockIdx.y == 0 ? out0 : out1;
   const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  if (c < C)
-    for (int r = ph; r < nparts; r += 8) acc += part[(size_t)r * C + c];
+  if (c < C) {
+    int r = ph;
+    for (; r + 96 < nparts; r += 128) {
+      const float v0 = part[(size_t)r * C + c], v1 = part[(size_t)(r + 32) * C + c];
+      const float v2 = part[(size_t)(r + 64) * C + c], v3 = part[(size_t)(r + 96) * C + c];
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; r < nparts; r += 32) acc += part[(size_t)r * C + c];
+  }
   s[ph][lane] = acc;
   __syncthreads();
   if (ph == 0 && c < C) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += s[k][lane];
+    for (int k = 0; k < 32; ++k) t += s[k][lane];
     out[c] = accumulate ? out[c] + t : t;
   }
 }
@@ -178,8 +186,8 @@ __global__ void __launch_bounds__(256) colsum_stage1_kernel(const T* __restrict_
 int ln_bwd_v4_launch(const void* dy, const void* xs, const float* mean, const float* rstd, const float* gamma,
                      const void* dres, void* dxs, void* dr, const float* rs, int rows_per_sample, float* pg, float* pb,
                      int grid, long long rows, int C, int sdtype, int cdtype, cudaStream_t st);
-int colsum_v8_launch(const void* a, long long rows, int C, float* part, int rows_per_cta, int parts, int dtype,
-                     cudaStream_t st);
+int colsum_v8_launch(const void* a, long long rows, int C, float* part, int dtype, cudaStream_t st);
+void colsum_plan(long long rows, int C, int* gx, int* TX, int* rows_per_cta, int* parts);
 int ln_fwd_v4_launch(const void* x, const void* r, const float* rs, int rows_per_sample, const float* gamma, const float* beta,
                      void* xs_out, void* y, float* mean, float* rstd, long long rows, int C, float eps, int sdtype, int cdtype,
                      cudaStream_t st);
@@ -243,7 +251,7 @@ int apb_ln_bwd(const void* dy, const void* xs, const float* mean, const float* r
                                          sdtype, cdtype, st);
     if (handled == 1) {
       APB_LAUNCH_CHECK("ln_bwd_v4");
-      colsum_partials_kernel<<<dim3(ceil_div(C, 32), 2), 256, 0, st>>>(pg, dgamma, pb, dbeta, grid, C, accumulate);
+      colsum_partials_kernel<<<dim3(ceil_div(C, 32), 2), 1024, 0, st>>>(pg, dgamma, pb, dbeta, grid, C, accumulate);
       APB_LAUNCH_CHECK("ln_bwd_reduce");
       return 0;
     }
@@ -273,14 +281,17 @@ int apb_ln_bwd(const void* dy, const void* xs, const float* mean, const float* r
 #undef LN_BWD
 #undef LN_BWD_NV
   APB_LAUNCH_CHECK("ln_bwd");
-  colsum_partials_kernel<<<dim3(ceil_div(C, 32), 2), 256, 0, st>>>(pg, dgamma, pb, dbeta, grid, C, accumulate);
+  colsum_partials_kernel<<<dim3(ceil_div(C, 32), 2), 1024, 0, st>>>(pg, dgamma, pb, dbeta, grid, C, accumulate);
   APB_LAUNCH_CHECK("ln_bwd_reduce");
   return 0;
 }
 
 long long apb_colsum_workspace_floats(long long rows, int C) {
-  const int parts = (int)((rows + 511) / 512);
-  return (long long)parts * C;
+  if (rows <= 0 || C <= 0) return 0;
+  int gx, TX, rpc, parts;
+  colsum_plan(rows, C, &gx, &TX, &rpc, &parts);
+  const long long scalar_parts = (rows + 511) / 512;       // fallback kernel (C % 8 != 0 or unaligned)
+  return (long long)(parts > scalar_parts ? parts : scalar_parts) * C;
 }
 
 // out[c] = sum_r a[r][c]  (bias gradients; batch reduction of the pos-embed gradient)
@@ -288,15 +299,19 @@ int apb_colsum(const void* a, long long rows, int C, float* out, int accumulate,
                apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
   if (rows <= 0 || C <= 0) return 0;
-  const int rows_per_cta = 512;
-  const int parts = (int)((rows + rows_per_cta - 1) / rows_per_cta);
-  if (colsum_v8_launch(a, rows, C, workspace, rows_per_cta, parts, dtype, st) != 1) {
+  int parts;
+  if (colsum_v8_launch(a, rows, C, workspace, dtype, st) == 1) {
+    int gx, TX, rpc;
+    colsum_plan(rows, C, &gx, &TX, &rpc, &parts);
+  } else {
+    const int rows_per_cta = 512;
+    parts = (int)((rows + rows_per_cta - 1) / rows_per_cta);
     dim3 grid(ceil_div(C, 32), parts);
     if (dtype == APB_F32) colsum_stage1_kernel<float><<<grid, 256, 0, st>>>((const float*)a, rows, C, workspace, rows_per_cta);
     else colsum_stage1_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)a, rows, C, workspace, rows_per_cta);
   }
   APB_LAUNCH_CHECK("colsum_stage1");
-  colsum_partials_kernel<<<dim3(ceil_div(C, 32), 1), 256, 0, st>>>(workspace, out, nullptr, nullptr, parts, C, accumulate);
+  colsum_partials_kernel<<<dim3(ceil_div(C, 32), 1), 1024, 0, st>>>(workspace, out, nullptr, nullptr, parts, C, accumulate);
   APB_LAUNCH_CHECK("colsum_stage2");
   return 0;
 }

@@ -161,48 +161,70 @@ __global__ void __launch_bounds__(256) ln_fwd_v4_kernel(const TS* __restrict__ x
   if (lane == 0 && mean != nullptr) { mean[row] = mu; rstd[row] = rs_; }
 }
 
-// column sums, stage 1: lane = 8 consecutive columns (16-byte loads for bf16), warp = 256 columns, warps stride the rows
+// column sums, stage 1.  A thread owns 8 consecutive columns (16-byte bf16 loads); TX threads span the CTA's column
+// slice and the remaining 256 / TX thread rows stride the CTA's row range with 4 rows in flight each.  The host picks
+// TX from C so narrow matrices (C = 192: TX = 24, 10 thread rows) keep every lane busy, and rows_per_cta so the grid
+// is several CTAs per SM -- the kernel is a pure HBM / L2 stream.
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w; v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    v[2 * j] = f.x; v[2 * j + 1] = f.y;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_v8_kernel(const T* __restrict__ a, long long rows, int C,
-                                                        float* __restrict__ part, int rows_per_cta) {
-  __shared__ float s[8][256 + 8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 256 + lane * 8;
-  const bool ok = c0 < C;
-  const int cc = ok ? c0 : 0;
+                                                        float* __restrict__ part, int rows_per_cta, int TX) {
+  __shared__ __align__(16) float s[256 * 8];              // [TY][TX * 8]
+  const int TY = 256 / TX;
+  const int ty = threadIdx.x / TX, tx = threadIdx.x - ty * TX;
+  const int c0 = (blockIdx.x * TX + tx) * 8;
+  const bool ok = ty < TY && c0 < C;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
   const long long r1 = min(rows, r0 + (long long)rows_per_cta);
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  long long r = r0 + warp;
-  for (; r + 24 < r1; r += 32) {        // 4 rows in flight per warp
-    float4 lo[4], hi[4];
+  if (ok) {
+    const T* col = a + c0;
+    long long r = r0 + ty;
+    for (; r + 3 * TY < r1; r += 4 * TY) {
+      float v[4][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      lo[u] = ld4(a + (size_t)(r + 8 * u) * C + cc);
-      hi[u] = ld4(a + (size_t)(r + 8 * u) * C + cc + 4);
+      for (int u = 0; u < 4; ++u) ld8(col + (size_t)(r + u * TY) * C, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[u][j];
     }
+    for (; r < r1; r += TY) {
+      float v[8];
+      ld8(col + (size_t)r * C, v);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      acc[0] += lo[u].x; acc[1] += lo[u].y; acc[2] += lo[u].z; acc[3] += lo[u].w;
-      acc[4] += hi[u].x; acc[5] += hi[u].y; acc[6] += hi[u].z; acc[7] += hi[u].w;
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
     }
   }
-  for (; r < r1; r += 8) {
-    const float4 lo = ld4(a + (size_t)r * C + cc), hi = ld4(a + (size_t)r * C + cc + 4);
-    acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w;
-    acc[4] += hi.x; acc[5] += hi.y; acc[6] += hi.z; acc[7] += hi.w;
+  if (ty < TY) {
+    float4* d = reinterpret_cast<float4*>(s + (ty * TX + tx) * 8);
+    d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s[warp][lane * 8 + j] = acc[j];
   __syncthreads();
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < C) {
-    float t = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) t += s[k][threadIdx.x];
-    part[(size_t)blockIdx.y * C + c] = t;
+  const int W = TX * 8;
+  for (int e = threadIdx.x; e < W; e += 256) {
+    const int c = blockIdx.x * W + e;
+    if (c < C) {
+      float t = 0.f;
+      for (int k = 0; k < TY; ++k) t += s[k * W + e];     // fixed order
+      part[(size_t)blockIdx.y * C + c] = t;
+    }
   }
 }
 
@@ -296,12 +318,26 @@ int ln_fwd_v4_launch(const void* x, const void* r, const float* rs, int rows_per
   return 1;
 }
 
-int colsum_v8_launch(const void* a, long long rows, int C, float* part, int rows_per_cta, int parts, int dtype,
-                     cudaStream_t st) {
+// stage-1 geometry shared by the launcher and apb_colsum_workspace_floats
+void colsum_plan(long long rows, int C, int* gx, int* TX, int* rows_per_cta, int* parts) {
+  const int groups = (C + 7) / 8;
+  *gx = (groups + 255) / 256;
+  *TX = (groups + *gx - 1) / *gx;
+  const int TY = 256 / *TX;
+  const long long want = (148 * 6) / *gx;                  // ~6 CTAs per SM
+  long long rpc = (rows + want - 1) / want;
+  if (rpc < 4LL * TY) rpc = 4LL * TY;
+  *rows_per_cta = (int)rpc;
+  *parts = (int)((rows + rpc - 1) / rpc);
+}
+
+int colsum_v8_launch(const void* a, long long rows, int C, float* part, int dtype, cudaStream_t st) {
   if ((C & 7) != 0 || ((uintptr_t)a & 15)) return 0;
-  dim3 grid(ceil_div(C, 256), parts);
-  if (dtype == APB_F32) colsum_v8_kernel<float><<<grid, 256, 0, st>>>((const float*)a, rows, C, part, rows_per_cta);
-  else if (dtype == APB_BF16) colsum_v8_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)a, rows, C, part, rows_per_cta);
+  int gx, TX, rpc, parts;
+  colsum_plan(rows, C, &gx, &TX, &rpc, &parts);
+  dim3 grid(gx, parts);
+  if (dtype == APB_F32) colsum_v8_kernel<float><<<grid, 256, 0, st>>>((const float*)a, rows, C, part, rpc, TX);
+  else if (dtype == APB_BF16) colsum_v8_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)a, rows, C, part, rpc, TX);
   else return 0;
   return 1;
 }

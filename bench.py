@@ -192,7 +192,8 @@ def main():
         try:
             from autoprog_b200.graph import GraphedTrainStep
             graphed = GraphedTrainStep(net, crit, opt, x_dev, t_dev, bf16=bf16, warmup=3)
-            graph_note = 'whole step replayed from one CUDA graph'
+            graph_note = ('whole step replayed from one CUDA graph' if world == 1 else
+                          'two CUDA graphs per step (fwd+bwd | optimizer+EMA) around one eager bucketed NCCL all-reduce')
         except Exception as e:   # noqa: BLE001 - fall back to eager launches, say so in the JSON line
             graphed, graph_note = None, f'eager launches (graph capture failed: {type(e).__name__}: {str(e)[:80]})'
             model._graph_box = None
@@ -368,14 +369,22 @@ def measure_rooflines(train_step, x, t, K, torch, B, bf16):
         return inner
 
     es = 2 if bf16 else 4
-    K.gemm = wrap('gemm', lambda a, b, M, N, Kd, **kw: (2.0 * M * N * Kd, (M, N, Kd, int(kw.get('trans_a', False)), int(kw.get('trans_b', False)), kw.get('epilogue', 0))))
+    def gemm_work(a, b, M, N, Kd, **kw):
+        oes = 4 if kw.get('out_dtype') == torch.float32 or (kw.get('out') is not None and kw['out'].dtype == torch.float32) else a.element_size()
+        nout = 2 if kw.get('epilogue', 0) != K.EPI_NONE else 1          # GELU stores gelu'(u); dGELU / ACC read one M x N operand
+        byts = (M * Kd + N * Kd) * a.element_size() + nout * M * N * oes
+        return (2.0 * M * N * Kd, (M, N, Kd, int(kw.get('trans_a', False)), int(kw.get('trans_b', False)), kw.get('epilogue', 0)), byts)
+    K.gemm = wrap('gemm', gemm_work)
     K.outlook_fwd = wrap('outlook_fwd', lambda v, lg, *a, **kw: (2 * v.numel() + lg.numel()) * es)
     K.outlook_bwd = wrap('outlook_bwd', lambda v, lg, *a, **kw: (3 * v.numel() + 2 * lg.numel()) * es)
     K.tlce_fwd_bwd = wrap('tlce', lambda xc, xa, *a, **kw: xa.numel() * (2 * es + 4))
     try:
-        for _ in range(2):            # first pass warms the caching allocator (host stalls would inflate event spans)
+        for _ in range(2):            # first pass warms the caching allocator
             for v in rec.values():
                 v.clear()
+            # park the GPU while the host enqueues the step: every event pair then brackets back-to-back device work
+            # only (an eager host that falls behind would otherwise leave idle time inside the spans)
+            torch.cuda._sleep(int(80e6))
             train_step(x, t)
             torch.cuda.synchronize()
     finally:
@@ -383,11 +392,16 @@ def measure_rooflines(train_step, x, t, K, torch, B, bf16):
 
     if os.environ.get('APB_BENCH_GEMM_TABLE'):
         tab = {}
-        for e0, e1, (w, key) in rec['gemm']:
-            t = tab.setdefault(key, [0, 0.0, 0.0])
-            t[0] += 1; t[1] += e0.elapsed_time(e1); t[2] += w
-        for key, (n, ms, w) in sorted(tab.items(), key=lambda kv: -kv[1][1]):
-            print(f'[gemm] M,N,K,ta,tb,epi={key} x{n}: {ms:.3f} ms  {w / ms / 1e9:.0f} TFLOP/s', file=sys.stderr)
+        for e0, e1, (w, key, by) in rec['gemm']:
+            t = tab.setdefault(key, [0, 0.0, 0.0, 0.0])
+            t[0] += 1; t[1] += e0.elapsed_time(e1); t[2] += w; t[3] += by
+        for key, (n, ms, w, by) in sorted(tab.items(), key=lambda kv: -kv[1][1]):
+            print(f'[gemm] M,N,K,ta,tb,epi={key} x{n}: {ms:.3f} ms  {w / ms / 1e9:.0f} TFLOP/s  {by / ms / 1e6:.0f} GB/s', file=sys.stderr)
+    # per launch: the roof that binds is max(flops / tensor peak, algorithmic bytes / HBM peak)
+    roof_ms = sum(max(w / (peaks['bf16_tflops_sustained'] * 1e9), by / (peaks['hbm_gbs'] * 1e6)) for _, _, (w, _, by) in rec['gemm'])
+    hbm_bound_ms = sum(e0.elapsed_time(e1) for e0, e1, (w, _, by) in rec['gemm']
+                       if by / (peaks['hbm_gbs'] * 1e6) > w / (peaks['bf16_tflops_sustained'] * 1e9))
+    gemm_bytes = sum(by for _, _, (_, _, by) in rec['gemm'])
     rec['gemm'] = [(e0, e1, w[0]) for e0, e1, w in rec['gemm']]
 
     def agg(name):
@@ -400,7 +414,12 @@ def measure_rooflines(train_step, x, t, K, torch, B, bf16):
     roof = {'kernel': 'gemm_tc_kernel (tcgen05) over all Linear/patchify GEMMs of one step', 'bound': 'tensor',
             'achieved': round(tf, 1), 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
             'frac': round(tf / peaks['bf16_tflops_sustained'], 4), 'traffic': None, 'launches_per_step': gn,
-            'ms_per_step': round(gms, 3), 'peak_source': peaks['src'] + ' (sustained cuBLAS bf16)'}
+            'ms_per_step': round(gms, 3), 'peak_source': peaks['src'] + ' (sustained cuBLAS bf16)',
+            # the step's GEMMs are a mix: K=192 layers of stage 1 are HBM-bound, the rest tensor-bound.  frac_binding =
+            # sum over launches of max(flop time at tensor peak, algorithmic-byte time at HBM peak) / measured time
+            'frac_binding': round(roof_ms / gms, 4) if gms > 0 else None,
+            'hbm_bound_share_of_ms': round(hbm_bound_ms / gms, 3) if gms > 0 else None,
+            'algorithmic_gbytes': round(gemm_bytes / 1e9, 3)}
     extra = {}
     fms, fby, fn_ = agg('outlook_fwd')
     bms, bby, _ = agg('outlook_bwd')
