@@ -30,6 +30,7 @@ struct TcParams {
   void* C;
   const float* bias;
   void* aux;
+  float* rowsum;        // optional [splits][M]: sum_k A(m,k) of this split's k-range (bias gradient of a wgrad GEMM)
   int M, N, K;
   int a_mn, b_mn;       // operand majors (1 = MN-major)
   int epilogue;         // 0 none, 1 gelu, 2 dgelu, 4 split-k partial
@@ -93,6 +94,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  return r;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -153,7 +159,9 @@ __device__ __forceinline__ uint8_t* stg64(uint8_t* stg, int row, int chunk) {
   return stg + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
 }
 
-template <int BN, int STAGES, int EPI_WARPS>
+// AUX = the epilogue needs the per-warp gelu' boxes (GELU / dGELU).  Without them the shared memory they would take
+// becomes one more pipeline stage: the main loop is bound by bytes in flight from L2, not by the tensor pipe.
+template <int BN, int STAGES, int EPI_WARPS, bool AUX>
 __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                              const __grid_constant__ CUtensorMap tma_b,
                                                              const __grid_constant__ CUtensorMap tma_c,
@@ -161,11 +169,14 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
   constexpr uint32_t A_BYTES = BM * BK * 2;   // 16 KB
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr uint32_t TMEM_COLS = (ACC_STAGES * BN <= 256) ? 256 : 512;   // power of two >= 2 accumulator stages
+  constexpr uint32_t RS_COLS = 16;                                        // row-sum accumulator: one N = 16 MMA per k-step
+  constexpr uint32_t TMEM_COLS = (ACC_STAGES * (BN + RS_COLS) <= 256) ? 256 : 512;   // power of two >= 2 accumulator stages
+  constexpr uint32_t ONES_BYTES = AUX ? 0 : 2048;                         // 16 rows x 128 B of bf16 1.0 (the "B operand" of the row sum)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr uint32_t STG_BYTES = 4096 + ((BN / 32) / (EPI_WARPS / 4)) * 2048;   // per epilogue warp: 4 KB of C boxes + one 2 KB aux box per chunk
-  uint8_t* stg_base = smem + STAGES * STAGE_BYTES;
+  constexpr uint32_t STG_BYTES = 4096 + (AUX ? ((BN / 32) / (EPI_WARPS / 4)) * 2048 : 0);   // per epilogue warp: 4 KB of C boxes (+ one 2 KB aux box per chunk)
+  uint8_t* ones = smem + STAGES * STAGE_BYTES;
+  uint8_t* stg_base = ones + ONES_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + EPI_WARPS * STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -176,6 +187,10 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
   const int total_kb = (p.K + BK - 1) / BK;
   const int n_items = p.tiles_m * p.tiles_n * p.splits;
 
+  if (!AUX && p.rowsum != nullptr) {
+    for (int i = threadIdx.x; i < (int)(ONES_BYTES / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA's async proxy
+  }
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
@@ -232,14 +247,19 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
       const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;
+      // row sums ride on the tensor pipe: one extra 128 x 16 x 16 MMA per k-step against a tile of ones (n-tile 0 only)
+      const uint32_t idesc_rs = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)(RS_COLS >> 3) << 17) |
+                                ((uint32_t)(BM >> 4) << 24);
+      const uint64_t ones_desc = make_smem_desc(smem_u32(ones), 16, 1024);
       uint32_t it = 0, ai = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ai) {
         const int z = item % p.splits;
+        const bool do_rs = !AUX && p.rowsum != nullptr && ((item / p.splits) % p.tiles_n) == 0;
         const int kb0 = z * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
         const uint32_t as = ai % ACC_STAGES;
         mbar_wait(&tempty_bar[as], ((ai / ACC_STAGES) & 1) ^ 1);      // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem_base + as * BN;
+        const uint32_t tacc = tmem_base + as * BN, trs = tmem_base + ACC_STAGES * BN + as * RS_COLS;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&full_bar[s], (it / STAGES) & 1);
@@ -250,6 +270,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
             const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
             umma_bf16(tacc, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (do_rs) umma_bf16(trs, ad, ones_desc, idesc_rs, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);   // frees the smem stage once the MMAs above have read it
         }
@@ -270,7 +291,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       const uint32_t as = ai % ACC_STAGES;
       const int rb = m0 + quarter * 32;           // first row of this warp's sub-tile
       const int cb0 = n0 + cg * NCH * 32;         // first column
-      if (p.epilogue == 2 && rb < p.M) {
+      if (AUX && p.epilogue == 2 && rb < p.M) {
         // dGELU: fetch the gelu'(pre-activation) sub-tiles (coalesced, 4 lanes per 64-byte row) while this tile's MMAs run
         const bf16* ax = reinterpret_cast<const bf16*>(p.aux);
 #pragma unroll
@@ -292,6 +313,9 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
 #pragma unroll
       for (int c = 0; c < NCH; ++c)
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)((cg * NCH + c) * 32), r[c]);
+      const bool rs_here = !AUX && p.rowsum != nullptr && cg == 0 && (t % p.tiles_n) == 0;   // warp-uniform
+      uint32_t rsv = 0;
+      if (rs_here) rsv = tmem_ld1(tmem_base + ((uint32_t)(quarter * 32) << 16) + ACC_STAGES * BN + as * RS_COLS);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -300,6 +324,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous TMA stores have drained the staging boxes
       }
       __syncwarp();
+      if (rs_here && rb + lane < p.M) p.rowsum[(size_t)z * p.M + rb + lane] = __uint_as_float(rsv);
       if (rb >= p.M) continue;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -317,7 +342,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
               v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
             }
         }
-        if (p.epilogue == 2) {
+        if (AUX && p.epilogue == 2) {
           __syncwarp();                             // prefetched gelu' sub-tile is complete
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
@@ -329,7 +354,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
               v[ch * 8 + 2 * tt + 1] *= __bfloat162float(h2[tt].y);
             }
           }
-        } else if (p.epilogue == 1) {
+        } else if (AUX && p.epilogue == 1) {
           // GELU: C = gelu(v); aux = gelu'(v) (what the dgrad epilogue multiplies by); Phi and the Gaussian are shared
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
@@ -371,7 +396,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         __syncwarp();
         if (lane == 0) {
           tma_store_3d(&tma_c, sc, cb, rb, z);
-          if (p.epilogue == 1) tma_store_3d(&tma_x, sx, cb, rb, 0);
+          if (AUX && p.epilogue == 1) tma_store_3d(&tma_x, sx, cb, rb, 0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -454,13 +479,14 @@ int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, int EPI_WARPS>
+template <int BN, int STAGES, int EPI_WARPS, bool AUX>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mx, TcParams p, int splits,
            cudaStream_t st) {
-  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + EPI_WARPS * (4096 + ((BN / 32) / (EPI_WARPS / 4)) * 2048) + 1024 + 256;
+  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + (AUX ? 0 : 2048) + EPI_WARPS * (4096 + (AUX ? ((BN / 32) / (EPI_WARPS / 4)) * 2048 : 0)) + 1024 + 256;
+  static_assert(smem <= 227 * 1024, "gemm_tc: shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI_WARPS, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { apb_set_error("gemm_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
@@ -469,7 +495,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
   p.splits = splits;
   const long long items = (long long)p.tiles_m * p.tiles_n * splits;
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  gemm_tc_kernel<BN, STAGES, EPI_WARPS><<<grid, 64 + EPI_WARPS * 32, smem, st>>>(ma, mb, mc, mx, p);
+  gemm_tc_kernel<BN, STAGES, EPI_WARPS, AUX><<<grid, 64 + EPI_WARPS * 32, smem, st>>>(ma, mb, mc, mx, p);
   APB_LAUNCH_CHECK("gemm_tc");
   return 0;
 }
@@ -477,8 +503,11 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
 }  // namespace
 
 // split_k > 1: C must hold split_k fp32 partials [split_k][M][N]; bias/epilogue are ignored.
-int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* aux, int M, int N, int K, int trans_a,
-                int trans_b, int epilogue, int in_dtype, int out_dtype, int split_k, apb_stream_t stream) {
+// rowsum_parts (optional): fp32 [split_k][M], receives sum_k A(m,k) per split -- the bias gradient of a wgrad GEMM
+// (A = dY^T), computed on the tensor pipe from the operand tiles already in shared memory.
+int apb_gemm_tc_rowsum(const void* A, const void* B, void* C, const float* bias, void* aux, int M, int N, int K, int trans_a,
+                       int trans_b, int epilogue, int in_dtype, int out_dtype, int split_k, float* rowsum_parts,
+                       apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
   APB_CHECK_ARG(in_dtype == APB_BF16, APB_ERR_DTYPE, "gemm_tc: inputs must be bf16 (got %d)", in_dtype);
   APB_CHECK_ARG(out_dtype == APB_BF16 || out_dtype == APB_F32, APB_ERR_DTYPE, "gemm_tc: out dtype %d", out_dtype);
@@ -508,7 +537,7 @@ int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* 
   if (!trans_b) rc = make_map(&mb, B, N, K, BN, BK); else rc = make_map(&mb, B, K, N, BK, 64);
   if (rc) return rc;
   TcParams p;
-  p.C = C; p.bias = bias; p.aux = aux; p.M = M; p.N = N; p.K = K; p.a_mn = trans_a ? 1 : 0; p.b_mn = trans_b ? 1 : 0;
+  p.C = C; p.bias = bias; p.aux = aux; p.rowsum = rowsum_parts; p.M = M; p.N = N; p.K = K; p.a_mn = trans_a ? 1 : 0; p.b_mn = trans_b ? 1 : 0;
   p.epilogue = splits > 1 ? 4 : epilogue;
   p.out_f32 = (out_dtype == APB_F32) ? 1 : 0;
   p.kb_per_split = kb_per;
@@ -521,8 +550,15 @@ int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* 
   if (rc) return rc;
   rc = make_map_out(&mx, (epilogue == 1) ? aux : C, (epilogue == 1) ? false : (p.out_f32 != 0), M, N, (epilogue == 1) ? 1 : splits);
   if (rc) return rc;
-  if (BN == 192) return launch<192, 3, 12>(ma, mb, mc, mx, p, splits, st);
-  return launch<128, 4, 16>(ma, mb, mc, mx, p, splits, st);
+  const bool aux_epi = (p.epilogue == 1 || p.epilogue == 2);
+  APB_CHECK_ARG(!(aux_epi && rowsum_parts != nullptr), APB_ERR_UNSUPPORTED, "gemm_tc: row sums are not available with GELU epilogues");
+  if (BN == 192) return aux_epi ? launch<192, 3, 12, true>(ma, mb, mc, mx, p, splits, st) : launch<192, 4, 12, false>(ma, mb, mc, mx, p, splits, st);
+  return aux_epi ? launch<128, 4, 16, true>(ma, mb, mc, mx, p, splits, st) : launch<128, 4, 16, false>(ma, mb, mc, mx, p, splits, st);
+}
+
+int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* aux, int M, int N, int K, int trans_a,
+                int trans_b, int epilogue, int in_dtype, int out_dtype, int split_k, apb_stream_t stream) {
+  return apb_gemm_tc_rowsum(A, B, C, bias, aux, M, N, K, trans_a, trans_b, epilogue, in_dtype, out_dtype, split_k, nullptr, stream);
 }
 
 // number of K splits the wgrad-shaped GEMM should use to fill the GPU (host helper for the binding)

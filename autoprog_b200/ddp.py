@@ -77,6 +77,12 @@ class DistributedDataParallel(nn.Module):
         if not self._armed:
             self._armed = True
             torch.autograd.Variable._execution_engine.queue_callback(self._finalize)
+        # a gradient that autograd allocated itself (not written in place by a kernel, see ops.grad_dest) must be in the
+        # flat buffer BEFORE its bucket's all-reduce is launched
+        view = getattr(p, '_apb_grad_view', None)
+        if view is not None and p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+            view.copy_(p.grad)
+            p.grad = view
         b = self.buckets[self._bucket_of[p]]
         b.ready += 1
         if b.ready == b.n_params:
@@ -105,6 +111,7 @@ class DistributedDataParallel(nn.Module):
         """Synchronous reduction of all buckets (for callers that run backward under `no_sync`)."""
         if self.world == 1:
             return
+        self.flat.ensure_grad_views()               # gradients autograd allocated itself -> flat buffer, before reducing
         for b in self.buckets:
             self._launch(b)
         self._finalize()

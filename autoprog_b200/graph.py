@@ -3,9 +3,11 @@
 The reference launches ~1300 kernels per step from Python and synchronises every step (main_prog.py:1035); at the
 early AutoProg stages (128-160 px, depth 9-12) the GPU work per step is shorter than the host's launch time.  A
 `GraphedTrainStep` captures zero-grad + forward + loss + backward + fused optimizer/EMA step ONCE per (resolution,
-depth, batch) configuration and replays it.  Everything that changes between steps is read from memory at replay
-time: the mix-token box (host RNG -> pinned int32[4] -> device, read by the flip and loss kernels), the optimizer's
-lr / bias corrections (pinned -> device), DropPath masks (CUDA RNG is graph-safe), inputs (static buffers).
+depth, batch) configuration and replays it.  Everything that changes between steps is read from DEVICE memory at
+replay time: the mix-token box (host RNG -> pinned ring slot -> device int32[4], read by the flip and loss kernels),
+the optimizer's lr / bias corrections (same staging), DropPath masks (CUDA RNG is graph-safe), inputs (static
+buffers).  The tiny host -> device copies are issued eagerly ahead of each replay from a ring of pinned slots
+(optim.PinnedRing), so the host may queue several steps ahead without overwriting a queued step's values.
 """
 from __future__ import annotations
 
@@ -13,6 +15,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .optim import PinnedRing
 from .volo import rand_bbox
 
 
@@ -28,14 +31,15 @@ class GraphedTrainStep:
         dev = example_input.device
         self.x = example_input.clone()
         self.t = example_target.clone()
-        self.box_host = torch.zeros(4, dtype=torch.int32).pin_memory()
-        self.box_dev = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.net._graph_box, self.net._graph_box_host = self.box_dev, self.box_host
+        self.box = PinnedRing((4,), torch.int32, dev)          # mix-token box: host RNG -> pinned slot -> device
+        self.box_dev = self.box.dev
+        self.net._graph_box, self.net._graph_box_host = self.box_dev, self.box.current()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 self._host_prepare()
+                self._stage()
                 self._device_step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -62,11 +66,17 @@ class GraphedTrainStep:
             s = net.pooling_scale
             g = self.x.shape[-1] // 8                      # stage-1 token grid
             box = rand_bbox((self.x.shape[0], g, g, 0), lam, scale=s)
-            self.box_host.copy_(torch.tensor([int(v) for v in box], dtype=torch.int32))
+            slot = self.box.next_slot()
+            slot.copy_(torch.tensor([int(v) for v in box], dtype=torch.int32))
+            self.net._graph_box_host = slot
         self.optimizer.prepare_step()
 
+    def _stage(self):
+        """Eager host -> device copies of the per-step scalars, queued ahead of the replay that reads them."""
+        self.box.push()
+        self.optimizer.stage_hyper()
+
     def _fwd_bwd(self):
-        self.box_dev.copy_(self.box_host, non_blocking=True)
         self.optimizer.zero_grad()
         with ops.autocast(enabled=self.bf16):
             out = self.model(self.x)
@@ -76,10 +86,13 @@ class GraphedTrainStep:
                 loss.backward()
         else:
             loss.backward()
+        # gradients that autograd allocated itself (e.g. the cuDNN stem convolutions) are copied into the flat buffer
+        # inside THIS captured segment: the eager all-reduce between the two graphs must already see them
+        self.optimizer.flat.ensure_grad_views()
         return loss.detach()
 
     def _opt_step(self):
-        self.optimizer.launch_step()
+        self.optimizer.launch_step(stage=False)
         self.optimizer.update_ema_buffers()
 
     def _device_step(self):
@@ -95,6 +108,7 @@ class GraphedTrainStep:
         if target is not None:
             self.t.copy_(target, non_blocking=True)
         self._host_prepare()
+        self._stage()
         self.graph.replay()
         if self.graph_opt is not None:
             self.ddp.reduce_now()

@@ -138,8 +138,11 @@ _FORCE_SIMT = False   # tests flip this to run the bf16 model on the CUDA-core G
 
 
 def gemm(a, b, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = False, bias=None, epilogue: int = EPI_NONE,
-         aux=None, out=None, out_dtype=None):
-    """C[M,N] = epi(A(m,k) B(n,k) + bias).  bf16 inputs -> tcgen05 kernel, fp32 inputs -> CUDA-core fp32 kernel."""
+         aux=None, out=None, out_dtype=None, rowsum_out=None):
+    """C[M,N] = epi(A(m,k) B(n,k) + bias).  bf16 inputs -> tcgen05 kernel, fp32 inputs -> CUDA-core fp32 kernel.
+
+    rowsum_out (fp32 [M], tcgen05 path only -- check `gemm_uses_tc` first): also receives sum_k A(m,k), i.e. the bias
+    gradient when this is the wgrad GEMM of a Linear (A = dY^T)."""
     assert a.dtype == b.dtype, (a.dtype, b.dtype)
     out_dtype = out_dtype or a.dtype
     if out is None:
@@ -147,8 +150,9 @@ def gemm(a, b, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = Fa
     if epilogue == EPI_GELU and aux is None:
         aux = torch.empty((M, N), device=a.device, dtype=out_dtype)
     assert a.numel() == M * K and b.numel() == N * K, (a.shape, b.shape, M, N, K)
-    use_tc = a.dtype == torch.bfloat16 and not _FORCE_SIMT and tc_supported(M, N, K)
+    use_tc = gemm_uses_tc(a, M, N, K)
     if not use_tc:
+        assert rowsum_out is None, 'rowsum_out needs the tcgen05 path'
         check(lib().apb_gemm_simt(_p(a), _p(b), _p(out), _p(bias), _p(aux), M, N, K, int(trans_a), int(trans_b), epilogue,
                                   dt(a), _CODES[out_dtype], _st()), 'gemm_simt')
         return (out, aux) if epilogue == EPI_GELU else out
@@ -157,13 +161,19 @@ def gemm(a, b, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = Fa
         split = int(lib().apb_gemm_tc_suggest_split(M, N, K))
     if split > 1:   # deterministic split-K: fp32 partial tiles, then a fixed-order sum over the split dim
         parts = torch.empty((split, M, N), device=a.device, dtype=torch.float32)
-        check(lib().apb_gemm_tc(_p(a), _p(b), _p(parts), None, None, M, N, K, int(trans_a), int(trans_b), 0, dt(a), F32,
-                                split, _st()), 'gemm_tc(split-k)')
-        check(lib().apb_splitk_reduce(_p(parts), _p(out), split, M * N, _st()), 'gemm_tc(split-k reduce)')
+        rparts = torch.empty((split, M), device=a.device, dtype=torch.float32) if rowsum_out is not None else None
+        check(lib().apb_gemm_tc_rowsum(_p(a), _p(b), _p(parts), None, None, M, N, K, int(trans_a), int(trans_b), 0, dt(a), F32,
+                                       split, _p(rparts), _st()), 'gemm_tc(split-k)')
+        check(lib().apb_splitk_reduce2(_p(parts), _p(out), M * N, _p(rparts), _p(rowsum_out), M if rparts is not None else 0,
+                                       split, _st()), 'gemm_tc(split-k reduce)')
         return out
-    check(lib().apb_gemm_tc(_p(a), _p(b), _p(out), _p(bias), _p(aux), M, N, K, int(trans_a), int(trans_b), epilogue, dt(a),
-                            _CODES[out_dtype], 1, _st()), 'gemm_tc')
+    check(lib().apb_gemm_tc_rowsum(_p(a), _p(b), _p(out), _p(bias), _p(aux), M, N, K, int(trans_a), int(trans_b), epilogue, dt(a),
+                                   _CODES[out_dtype], 1, _p(rowsum_out), _st()), 'gemm_tc')
     return (out, aux) if epilogue == EPI_GELU else out
+
+
+def gemm_uses_tc(a: torch.Tensor, M: int, N: int, K: int) -> bool:
+    return a.dtype == torch.bfloat16 and not _FORCE_SIMT and tc_supported(M, N, K)
 
 
 def tc_supported(M: int, N: int, K: int) -> bool:

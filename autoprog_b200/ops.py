@@ -107,9 +107,20 @@ def _lin_bwd(dy2d, x2d, w, need_dx=True, need_dw=True, need_db=True, dgelu_aux=N
     if need_dw:
         if dw_out is not None and tuple(dw_out.shape) != (N, Kd):
             dw_out = None
-        dw = K.gemm(dy2d, x2d, N, Kd, M, trans_a=True, trans_b=True, out_dtype=F32, out=dw_out)
+        if need_db and db_out is not None and db_out.numel() != N:
+            db_out = None
+        # bf16: the bias gradient (column sums of dY) is accumulated by the wgrad GEMM itself on the tensor pipe
+        fused_db = need_db and K.gemm_uses_tc(dy2d, N, Kd, M)
+        if fused_db:
+            db = db_out if db_out is not None else torch.empty(N, device=dy2d.device, dtype=F32)
+        dw = K.gemm(dy2d, x2d, N, Kd, M, trans_a=True, trans_b=True, out_dtype=F32, out=dw_out,
+                    rowsum_out=db if fused_db else None)
         if dw_out is not None:
             dw = dw.detach()       # fresh alias: autograd adopts it as `.grad` without cloning (sole reference)
+        if fused_db:
+            if db_out is not None:
+                db = db.detach()
+            need_db = False
     if need_db:
         if db_out is not None and db_out.numel() != N:
             db_out = None

@@ -17,6 +17,36 @@ from . import ops
 from .flat import FlatState
 
 
+class PinnedRing:
+    """Host -> device staging of a few per-step scalars (lr / bias corrections, the mix-token box) that kernels read
+    from DEVICE memory.  `slots` pinned host buffers feed one device buffer; a slot is rewritten only after the async
+    copy that read it has executed, so the host may run several steps ahead of the GPU without corrupting a step that
+    is still queued (a single pinned buffer would be overwritten by step i+1 before step i's copy has run)."""
+
+    def __init__(self, shape, dtype, device, slots: int = 8):
+        self.host = [torch.zeros(shape, dtype=dtype).pin_memory() for _ in range(slots)]
+        self.events: List[Optional[torch.cuda.Event]] = [None] * slots
+        self.dev = torch.zeros(shape, dtype=dtype, device=device)
+        self.i = 0
+
+    def next_slot(self) -> torch.Tensor:
+        """The host buffer to fill for the coming step."""
+        self.i = (self.i + 1) % len(self.host)
+        if self.events[self.i] is not None:
+            self.events[self.i].synchronize()
+        return self.host[self.i]
+
+    def current(self) -> torch.Tensor:
+        return self.host[self.i]
+
+    def push(self):
+        """Enqueue current host slot -> device buffer on the current stream (never inside a graph capture)."""
+        self.dev.copy_(self.host[self.i], non_blocking=True)
+        if self.events[self.i] is None:
+            self.events[self.i] = torch.cuda.Event()
+        self.events[self.i].record()
+
+
 class FusedAdamW(torch.optim.Optimizer):
     def __init__(self, model: nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.05,
                  ema_models: Sequence[nn.Module] = (), ema_decays: Sequence[float] = (), flat: Optional[FlatState] = None):
@@ -28,8 +58,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self.exp_avg_sq = [torch.zeros_like(g.flat_p) for g in self.flat.groups]
         self.step_count = 0
         dev = self.flat.groups[0].flat_p.device
-        self._hyper_host = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in self.flat.groups]
-        self._hyper_dev = [torch.zeros(3, device=dev, dtype=torch.float32) for _ in self.flat.groups]
+        self._hyper = PinnedRing((len(self.flat.groups), 3), torch.float32, dev)   # {lr, 1-b1^t, sqrt(1-b2^t)} per group
         self.ema_models = list(ema_models)
         self.ema_decays = [float(d) for d in ema_decays]
         self.ema_flats = [self.flat.flat_like(e) for e in self.ema_models]     # [ema][group] -> flat fp32
@@ -45,21 +74,27 @@ class FusedAdamW(torch.optim.Optimizer):
     def prepare_step(self):
         """Host part of a step: bump the step counter and stage {lr, bias corrections} in pinned memory."""
         self.step_count += 1
+        h = self._hyper.next_slot()
         for gi, group in enumerate(self.param_groups):
             b1, b2 = group['betas']
-            h = self._hyper_host[gi]
-            h[0] = group['lr']
-            h[1] = 1.0 - b1 ** self.step_count
-            h[2] = math.sqrt(1.0 - b2 ** self.step_count)
+            h[gi, 0] = group['lr']
+            h[gi, 1] = 1.0 - b1 ** self.step_count
+            h[gi, 2] = math.sqrt(1.0 - b2 ** self.step_count)
+
+    def stage_hyper(self):
+        """Enqueue this step's hyper-parameters host -> device (eager; graph replays read the device copy)."""
+        self._hyper.push()
 
     @torch.no_grad()
-    def launch_step(self):
-        """Device part of a step (CUDA-graph capturable: reads the pinned hyper-parameters at replay time)."""
+    def launch_step(self, stage: bool = True):
+        """Device part of a step.  stage=False: CUDA-graph capturable -- the kernels read lr / bias corrections from
+        device memory that `stage_hyper()` refreshes eagerly before every replay."""
         self.flat.ensure_grad_views()
+        if stage:
+            self.stage_hyper()
         for gi, (g, group) in enumerate(zip(self.flat.groups, self.param_groups)):
-            self._hyper_dev[gi].copy_(self._hyper_host[gi], non_blocking=True)
             b1, b2 = group['betas']
-            K.adamw_ema(g.flat_p, g.flat_g, self.exp_avg[gi], self.exp_avg_sq[gi], self._hyper_dev[gi], b1, b2, group['eps'],
+            K.adamw_ema(g.flat_p, g.flat_g, self.exp_avg[gi], self.exp_avg_sq[gi], self._hyper.dev[gi], b1, b2, group['eps'],
                         group['weight_decay'], [ef[gi] for ef in self.ema_flats], self.ema_decays, g.shadow)
         ops.invalidate_derived_caches()
 
