@@ -33,7 +33,8 @@ SIGNATURES = {
     'apb_gemm_tc_suggest_split': (_i, [_i, _i, _i]),
     'apb_splitk_reduce': (_i, [_vp, _vp, _i, _ll, _vp]),
     'apb_gemm_tc_rowsum': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
-    'apb_splitk_reduce2': (_i, [_vp, _vp, _ll, _vp, _vp, _ll, _i, _vp]),
+    'apb_gemm_tc_rowsum_slots': (_i, [_i, _i]),
+    'apb_splitk_reduce2': (_i, [_vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp]),
     'apb_mhsa_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_mhsa_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_mhsa_fwd_simt': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),

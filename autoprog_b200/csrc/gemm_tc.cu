@@ -30,7 +30,7 @@ struct TcParams {
   void* C;
   const float* bias;
   void* aux;
-  float* rowsum;        // optional [splits][M]: sum_k A(m,k) of this split's k-range (bias gradient of a wgrad GEMM)
+  float* rowsum;        // optional [splits * tiles_n][M]: partial sum_k A(m,k) (bias gradient of a wgrad GEMM)
   int M, N, K;
   int a_mn, b_mn;       // operand majors (1 = MN-major)
   int epilogue;         // 0 none, 1 gelu, 2 dgelu, 4 split-k partial
@@ -247,14 +247,16 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
       const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;
-      // row sums ride on the tensor pipe: one extra 128 x 16 x 16 MMA per k-step against a tile of ones (n-tile 0 only)
+      // row sums ride on the tensor pipe: one extra 128 x 16 x 16 MMA per k-step against a tile of ones.  The n-tiles
+      // of an m-tile read the same A tiles, so they share the work: n-tile j covers the k-blocks with kb % tiles_n == j
       const uint32_t idesc_rs = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)(RS_COLS >> 3) << 17) |
                                 ((uint32_t)(BM >> 4) << 24);
       const uint64_t ones_desc = make_smem_desc(smem_u32(ones), 16, 1024);
       uint32_t it = 0, ai = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ai) {
         const int z = item % p.splits;
-        const bool do_rs = !AUX && p.rowsum != nullptr && ((item / p.splits) % p.tiles_n) == 0;
+        const int tn = (item / p.splits) % p.tiles_n;
+        uint32_t rs_acc = 0;
         const int kb0 = z * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
         const uint32_t as = ai % ACC_STAGES;
         mbar_wait(&tempty_bar[as], ((ai / ACC_STAGES) & 1) ^ 1);      // epilogue has drained this accumulator
@@ -265,12 +267,23 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
           mbar_wait(&full_bar[s], (it / STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+          // two straight-line versions of the k-steps (no conditionally executed tensor-core instruction)
+          if (!AUX && p.rowsum != nullptr && (kb % p.tiles_n) == tn) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
-            const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16(tacc, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (do_rs) umma_bf16(trs, ad, ones_desc, idesc_rs, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+              const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+              umma_bf16(tacc, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_bf16(trs, ad, ones_desc, idesc_rs, rs_acc | (uint32_t)(k > 0));
+            }
+            rs_acc = 1u;
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+              const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+              umma_bf16(tacc, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[s]);   // frees the smem stage once the MMAs above have read it
         }
@@ -313,10 +326,13 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
 #pragma unroll
       for (int c = 0; c < NCH; ++c)
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + (uint32_t)((cg * NCH + c) * 32), r[c]);
-      const bool rs_here = !AUX && p.rowsum != nullptr && cg == 0 && (t % p.tiles_n) == 0;   // warp-uniform
+      const bool rs_here = !AUX && p.rowsum != nullptr && cg == 0;   // warp-uniform
+      // tcgen05.ld is asynchronous: its destination registers are valid only after wait::ld.  The row-sum load is issued
+      // unconditionally (no select on its result that the compiler could evaluate before the wait) and pinned below.
       uint32_t rsv = 0;
-      if (rs_here) rsv = tmem_ld1(tmem_base + ((uint32_t)(quarter * 32) << 16) + ACC_STAGES * BN + as * RS_COLS);
+      if (!AUX) rsv = tmem_ld1(tmem_base + ((uint32_t)(quarter * 32) << 16) + ACC_STAGES * BN + as * RS_COLS);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("" : "+r"(rsv)::"memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
@@ -324,7 +340,12 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous TMA stores have drained the staging boxes
       }
       __syncwarp();
-      if (rs_here && rb + lane < p.M) p.rowsum[(size_t)z * p.M + rb + lane] = __uint_as_float(rsv);
+      if (rs_here && rb + lane < p.M) {
+        const int tn = t % p.tiles_n;
+        const int kb0 = z * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+        const int first = kb0 + ((tn - kb0 % p.tiles_n) + p.tiles_n) % p.tiles_n;   // first k-block this n-tile summed
+        p.rowsum[((size_t)z * p.tiles_n + tn) * p.M + rb + lane] = first < kb1 ? __uint_as_float(rsv) : 0.f;
+      }
       if (rb >= p.M) continue;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -503,8 +524,9 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
 }  // namespace
 
 // split_k > 1: C must hold split_k fp32 partials [split_k][M][N]; bias/epilogue are ignored.
-// rowsum_parts (optional): fp32 [split_k][M], receives sum_k A(m,k) per split -- the bias gradient of a wgrad GEMM
-// (A = dY^T), computed on the tensor pipe from the operand tiles already in shared memory.
+// rowsum_parts (optional): fp32 [apb_gemm_tc_rowsum_slots(N, split_k)][M] partial sums whose total over the slot dim is
+// sum_k A(m,k) -- the bias gradient of a wgrad GEMM (A = dY^T), computed on the tensor pipe from the operand tiles
+// already in shared memory.
 int apb_gemm_tc_rowsum(const void* A, const void* B, void* C, const float* bias, void* aux, int M, int N, int K, int trans_a,
                        int trans_b, int epilogue, int in_dtype, int out_dtype, int split_k, float* rowsum_parts,
                        apb_stream_t stream) {
@@ -554,6 +576,11 @@ int apb_gemm_tc_rowsum(const void* A, const void* B, void* C, const float* bias,
   APB_CHECK_ARG(!(aux_epi && rowsum_parts != nullptr), APB_ERR_UNSUPPORTED, "gemm_tc: row sums are not available with GELU epilogues");
   if (BN == 192) return aux_epi ? launch<192, 3, 12, true>(ma, mb, mc, mx, p, splits, st) : launch<192, 4, 12, false>(ma, mb, mc, mx, p, splits, st);
   return aux_epi ? launch<128, 4, 16, true>(ma, mb, mc, mx, p, splits, st) : launch<128, 4, 16, false>(ma, mb, mc, mx, p, splits, st);
+}
+
+int apb_gemm_tc_rowsum_slots(int N, int split_k) {
+  const int bn = (ceil_div(N, 192) * 192 <= ceil_div(N, 128) * 128) ? 192 : 128;
+  return (split_k < 1 ? 1 : split_k) * ceil_div(N, bn);
 }
 
 int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* aux, int M, int N, int K, int trans_a,

@@ -232,13 +232,14 @@ __global__ void __launch_bounds__(256) colsum_v8_kernel(const T* __restrict__ a,
 // small job (the bias-gradient partials of the same GEMM) rides along in the same grid.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ parts, float* __restrict__ out, int splits,
                                                             long long n4, const float* __restrict__ parts2,
-                                                            float* __restrict__ out2, long long n4b) {
+                                                            float* __restrict__ out2, long long n4b, int splits2) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + n4b; i += (long long)gridDim.x * blockDim.x) {
     const bool second = i >= n4;
     const float4* src = reinterpret_cast<const float4*>(second ? parts2 : parts);
     const long long j = second ? i - n4 : i, stride = second ? n4b : n4;
     float4 acc = src[j];
-    for (int s = 1; s < splits; ++s) {
+    const int ns = second ? splits2 : splits;
+    for (int s = 1; s < ns; ++s) {
       const float4 v = src[(long long)s * stride + j];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
@@ -248,8 +249,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 
 }  // namespace
 
-int apb_splitk_reduce2(const float* parts, float* out, long long n, const float* parts2, float* out2, long long n2, int splits,
-                       apb_stream_t stream) {
+int apb_splitk_reduce2(const float* parts, float* out, long long n, int splits, const float* parts2, float* out2, long long n2,
+                       int splits2, apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
   APB_CHECK_ARG(splits >= 1 && n > 0 && (n % 4) == 0 && (((uintptr_t)parts | (uintptr_t)out) & 15) == 0, APB_ERR_ARG,
                 "splitk_reduce: splits=%d n=%lld (n must be a multiple of 4, pointers 16-byte aligned)", splits, n);
@@ -258,13 +259,13 @@ int apb_splitk_reduce2(const float* parts, float* out, long long n, const float*
   const long long n4 = n / 4, n4b = n2 / 4;
   long long grid = (n4 + n4b + 255) / 256;
   if (grid > 148 * 8) grid = 148 * 8;
-  splitk_reduce_kernel<<<(int)grid, 256, 0, st>>>(parts, out, splits, n4, parts2, out2, n4b);
+  splitk_reduce_kernel<<<(int)grid, 256, 0, st>>>(parts, out, splits, n4, parts2, out2, n4b, splits2 < 1 ? 1 : splits2);
   APB_LAUNCH_CHECK("splitk_reduce");
   return 0;
 }
 
 int apb_splitk_reduce(const float* parts, float* out, int splits, long long n, apb_stream_t stream) {
-  return apb_splitk_reduce2(parts, out, n, nullptr, nullptr, 0, splits, stream);
+  return apb_splitk_reduce2(parts, out, n, splits, nullptr, nullptr, 0, 1, stream);
 }
 
 // returns 1 if handled, 0 if the caller must use the scalar kernel, <0 / >1 on error

@@ -159,16 +159,19 @@ def gemm(a, b, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = Fa
     split = 1
     if out_dtype == torch.float32 and epilogue == EPI_NONE and bias is None:
         split = int(lib().apb_gemm_tc_suggest_split(M, N, K))
+    slots = int(lib().apb_gemm_tc_rowsum_slots(N, split)) if rowsum_out is not None else 0
+    rparts = torch.empty((slots, M), device=a.device, dtype=torch.float32) if slots > 1 else rowsum_out
     if split > 1:   # deterministic split-K: fp32 partial tiles, then a fixed-order sum over the split dim
         parts = torch.empty((split, M, N), device=a.device, dtype=torch.float32)
-        rparts = torch.empty((split, M), device=a.device, dtype=torch.float32) if rowsum_out is not None else None
         check(lib().apb_gemm_tc_rowsum(_p(a), _p(b), _p(parts), None, None, M, N, K, int(trans_a), int(trans_b), 0, dt(a), F32,
                                        split, _p(rparts), _st()), 'gemm_tc(split-k)')
-        check(lib().apb_splitk_reduce2(_p(parts), _p(out), M * N, _p(rparts), _p(rowsum_out), M if rparts is not None else 0,
-                                       split, _st()), 'gemm_tc(split-k reduce)')
+        check(lib().apb_splitk_reduce2(_p(parts), _p(out), M * N, split, _p(rparts), _p(rowsum_out), M if slots else 0, slots,
+                                       _st()), 'gemm_tc(split-k reduce)')
         return out
     check(lib().apb_gemm_tc_rowsum(_p(a), _p(b), _p(out), _p(bias), _p(aux), M, N, K, int(trans_a), int(trans_b), epilogue, dt(a),
-                                   _CODES[out_dtype], 1, _p(rowsum_out), _st()), 'gemm_tc')
+                                   _CODES[out_dtype], 1, _p(rparts), _st()), 'gemm_tc')
+    if slots > 1:
+        check(lib().apb_splitk_reduce(_p(rparts), _p(rowsum_out), slots, M, _st()), 'gemm_tc(row-sum reduce)')
     return (out, aux) if epilogue == EPI_GELU else out
 
 

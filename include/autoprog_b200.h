@@ -90,17 +90,19 @@ int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* 
 int apb_gemm_tc_suggest_split(int M, int N, int K);
 /* out[i] = sum_s parts[s][i] in fixed order (n % 4 == 0): the reduction of the split-K partials. */
 int apb_splitk_reduce(const float* parts, float* out, int splits, long long n, apb_stream_t stream);
-/* apb_gemm_tc plus rowsum_parts[split_k][M] (fp32) = sum_k A(m,k) over each split's k-range.  For the wgrad GEMM of
- * nn.Linear (A = dY^T, models/volo.py:67-71 etc. backward) that is the bias gradient: it is accumulated on the tensor
- * pipe (one extra 128x16x16 MMA per k-step against a tile of ones) from the dY tiles the GEMM has already staged in
- * shared memory, so no separate pass over dY is needed.  rowsum_parts may be NULL (== apb_gemm_tc). */
+/* apb_gemm_tc plus rowsum_parts[apb_gemm_tc_rowsum_slots(N, split_k)][M] (fp32): partial sums whose total over the slot
+ * dim is sum_k A(m,k).  For the wgrad GEMM of nn.Linear (A = dY^T, models/volo.py:67-71 etc. backward) that is the bias
+ * gradient: it is accumulated on the tensor pipe (one extra 128x16x16 MMA per k-step against a tile of ones, shared
+ * between the n-tiles of an m-tile) from the dY tiles the GEMM has already staged in shared memory, so no separate pass
+ * over dY is needed.  rowsum_parts may be NULL (== apb_gemm_tc). */
 int apb_gemm_tc_rowsum(const void* A, const void* B, void* C, const float* bias, void* aux, int M, int N, int K, int trans_a,
                        int trans_b, int epilogue, int in_dtype, int out_dtype, int split_k, float* rowsum_parts,
                        apb_stream_t stream);
+int apb_gemm_tc_rowsum_slots(int N, int split_k);
 /* apb_splitk_reduce over two partial sets in one launch (weight-gradient tiles + the bias-gradient row sums);
  * n2 == 0 disables the second job. */
-int apb_splitk_reduce2(const float* parts, float* out, long long n, const float* parts2, float* out2, long long n2, int splits,
-                       apb_stream_t stream);
+int apb_splitk_reduce2(const float* parts, float* out, long long n, int splits, const float* parts2, float* out2, long long n2,
+                       int splits2, apb_stream_t stream);
 
 /* ---- multi-head self-attention core  softmax(q k^T * scale) v  (models/volo.py:188-197)
  * qkv [B,N,3*heads*D] laid out (3, heads, D) per token; out [B,N,heads*D]; lse [B,heads,N] fp32 (saved for bwd).

@@ -330,6 +330,26 @@ def test_outlook_full_size_properties():
             assert rel(yu[:2], ref) < 1e-5
 
 
+@pytest.mark.parametrize('M,N,Kd,ta', [(384, 384, 25088, True), (1152, 384, 6272, True), (488, 192, 3136, True), (200, 136, 1000, True),
+                                       (64, 1000, 512, True), (256, 128, 64, False), (1000, 576, 192, False), (192, 192, 100352, True)])
+def test_gemm_tc_rowsum(M, N, Kd, ta):
+    """wgrad GEMM that also returns sum_k A(m,k) (the bias gradient), accumulated on the tensor pipe."""
+    dev = need_gpu()
+    torch.manual_seed(M + N + Kd)
+    a = q(torch.randn(M, Kd), torch.bfloat16)
+    b = q(torch.randn(N, Kd), torch.bfloat16)
+    A_ = (a.t().contiguous() if ta else a).to(dev, torch.bfloat16)
+    B_ = b.t().contiguous().to(dev, torch.bfloat16)
+    rs = torch.full((M,), float('nan'), device=dev)
+    out = K.gemm(A_, B_, M, N, Kd, trans_a=ta, trans_b=True, out_dtype=torch.float32, rowsum_out=rs)
+    assert rel(out, a @ b.t()) < 1e-5
+    rs_ref = a.sum(1)
+    assert float((rs.double().cpu() - rs_ref).abs().max()) < 1e-5 * float(rs_ref.abs().max()) + 1e-3 * (Kd ** 0.5) * 1e-3
+    rs2 = torch.empty_like(rs)
+    K.gemm(A_, B_, M, N, Kd, trans_a=ta, trans_b=True, out_dtype=torch.float32, rowsum_out=rs2)
+    assert torch.equal(rs, rs2)                                   # deterministic
+
+
 @pytest.mark.parametrize('ta,tb', [(False, False), (False, True), (True, True), (True, False)])
 @pytest.mark.parametrize('M,N,Kd', [(128, 128, 64), (256, 128, 192), (200, 136, 72), (1000, 384, 1152), (392, 1000, 384),
                                     (8, 8, 8), (130, 72, 200)])
