@@ -247,6 +247,53 @@ __global__ void gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ d
     dx[idx] = from_f<T>(to_f(dy[idx]) * dgelu_f(to_f(x[idx])));
 }
 
+
+// im2col for a small-channel convolution (the 7x7 / stride-2 stem conv, models/volo.py:352): row = output pixel
+// (b, oy, ox), column k = c * KH * KW + ky * KW + kx (the memory order of an nn.Conv2d weight row), zero beyond
+// C * KH * KW (columns are padded to a multiple of 8 for the TMA row pitch) and for taps outside the image.
+// One CTA per output row (b, oy): the C * KH input rows it needs are staged ONCE in shared memory (coalesced reads,
+// zero-filled borders), then every thread gathers 8 consecutive columns and writes them as one 16-byte store.
+// The input is read through arbitrary element strides (NCHW or NHWC, fp32 or bf16).
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const T* __restrict__ x, bf16* __restrict__ col, int C, int H, int W,
+                                                          int KH, int KW, int stride, int pad, int OH, int OW, int Kpad,
+                                                          long long sb, long long sc, long long sh, long long sw) {
+  extern __shared__ float srow[];                       // [C * KH][SW], SW = W + 2 * pad
+  const int SW = W + 2 * pad;
+  const int b = blockIdx.x / OH, oy = blockIdx.x - b * OH;
+  const int iy0 = oy * stride - pad;
+  const T* xb = x + (long long)b * sb;
+  const int nstage = C * KH * SW;
+  for (int e = threadIdx.x; e < nstage; e += 256) {
+    const int rr = e / SW, xx = e - rr * SW;            // rr = c * KH + ky
+    const int c = rr / KH, ky = rr - c * KH;
+    const int iy = iy0 + ky, ix = xx - pad;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = to_f(xb[c * sc + iy * sh + ix * sw]);
+    srow[e] = v;
+  }
+  __syncthreads();
+  const int chunks = Kpad >> 3, Kreal = C * KH * KW;
+  bf16* out = col + (size_t)blockIdx.x * OW * Kpad;
+  for (int e = threadIdx.x; e < OW * chunks; e += 256) {
+    const int ox = e / chunks, ch = e - ox * chunks;
+    const int k0 = ch * 8;
+    int rr = k0 / KW, kx = k0 - rr * KW;                // rr = c * KH + ky (rows of srow are in exactly this order)
+    const float* base = srow + ox * stride;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = (k0 + j < Kreal) ? base[rr * SW + kx] : 0.f;
+      if (++kx == KW) { kx = 0; ++rr; }
+    }
+    uint4 pk;
+    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out + (size_t)e * 8) = pk;
+  }
+}
+
 }  // namespace
 
 #define DISPATCH_T(dtype, name, CALL_F32, CALL_BF16)                                 \
@@ -483,5 +530,30 @@ int apb_gelu_bwd(const void* x, const void* dy, void* dx, long long n, int dtype
   DISPATCH_T(dtype, "gelu_bwd",
              (gelu_bwd_kernel<float><<<ew_grid(n), EW_THREADS, 0, st>>>((const float*)x, (const float*)dy, (float*)dx, n)),
              (gelu_bwd_kernel<bf16><<<ew_grid(n), EW_THREADS, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, n)));
+  return 0;
+}
+
+int apb_im2col(const void* x, void* col, int B, int C, int H, int W, int KH, int KW, int stride, int pad, int Kpad,
+               long long sb, long long sc, long long sh, long long sw, int in_dtype, apb_stream_t stream) {
+  cudaStream_t st = APB_STREAM(stream);
+  APB_CHECK_ARG(B > 0 && C > 0 && KH > 0 && KW > 0 && stride > 0 && pad >= 0, APB_ERR_SHAPE, "im2col: bad geometry");
+  APB_CHECK_ARG(Kpad % 8 == 0 && Kpad >= C * KH * KW, APB_ERR_SHAPE, "im2col: Kpad=%d must be a multiple of 8 >= %d", Kpad,
+                C * KH * KW);
+  APB_CHECK_ARG(((uintptr_t)col & 15) == 0, APB_ERR_ARG, "im2col: col must be 16-byte aligned");
+  const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
+  APB_CHECK_ARG(OH > 0 && OW > 0, APB_ERR_SHAPE, "im2col: empty output");
+  const size_t smem = (size_t)C * KH * (W + 2 * pad) * sizeof(float);
+  APB_CHECK_ARG(smem <= 200 * 1024, APB_ERR_UNSUPPORTED, "im2col: C*KH*(W+2*pad) = %zu floats do not fit shared memory",
+                smem / sizeof(float));
+  if (in_dtype == APB_F32) {
+    cudaFuncSetAttribute(im2col_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    im2col_rows_kernel<float><<<B * OH, 256, smem, st>>>((const float*)x, (bf16*)col, C, H, W, KH, KW, stride, pad, OH, OW, Kpad,
+                                                        sb, sc, sh, sw);
+  } else if (in_dtype == APB_BF16) {
+    cudaFuncSetAttribute(im2col_rows_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    im2col_rows_kernel<bf16><<<B * OH, 256, smem, st>>>((const bf16*)x, (bf16*)col, C, H, W, KH, KW, stride, pad, OH, OW, Kpad,
+                                                       sb, sc, sh, sw);
+  } else { apb_set_error("im2col: unsupported dtype %d", in_dtype); return APB_ERR_DTYPE; }
+  APB_LAUNCH_CHECK("im2col");
   return 0;
 }

@@ -439,7 +439,18 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// cuTensorMapEncodeTiled is a DRIVER call: it needs a current context on the calling thread.  Autograd worker threads
+// may reach a GEMM before any runtime call has bound the primary context there, so bind it once per thread.
+void ensure_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 EncodeTiledFn get_encode() {
+  ensure_context();
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -488,6 +499,13 @@ int make_map_out(CUtensorMap* map, const void* base, bool f32, long long M, long
     return APB_ERR_ARG;
   }
   return 0;
+}
+
+// tile width: 64 for narrow outputs (the stem conv, N = 64); 192 when it wastes no more columns than 128 (N = 192, 384,
+// 576, 768, 1152, ...): 20 % less L2 operand traffic per FLOP and fewer tiles; otherwise 128
+int pick_bn(int N) {
+  if (N <= 64) return 64;
+  return (ceil_div(N, 192) * 192 <= ceil_div(N, 128) * 128) ? 192 : 128;
 }
 
 int num_sms() {
@@ -553,9 +571,7 @@ int apb_gemm_tc_rowsum(const void* A, const void* B, void* C, const float* bias,
   int rc;
   if (!trans_a) rc = make_map(&ma, A, M, K, BM, BK); else rc = make_map(&ma, A, K, M, BK, 64);
   if (rc) return rc;
-  // tile width: 192 when it wastes no more columns than 128 (N = 192, 384, 576, 768, 1152, ...): 20 % less L2 operand
-  // traffic per FLOP and fewer tiles; otherwise 128
-  const int BN = (ceil_div(N, 192) * 192 <= ceil_div(N, 128) * 128) ? 192 : 128;
+  const int BN = pick_bn(N);
   if (!trans_b) rc = make_map(&mb, B, N, K, BN, BK); else rc = make_map(&mb, B, K, N, BK, 64);
   if (rc) return rc;
   TcParams p;
@@ -574,13 +590,13 @@ int apb_gemm_tc_rowsum(const void* A, const void* B, void* C, const float* bias,
   if (rc) return rc;
   const bool aux_epi = (p.epilogue == 1 || p.epilogue == 2);
   APB_CHECK_ARG(!(aux_epi && rowsum_parts != nullptr), APB_ERR_UNSUPPORTED, "gemm_tc: row sums are not available with GELU epilogues");
+  if (BN == 64) return aux_epi ? launch<64, 6, 8, true>(ma, mb, mc, mx, p, splits, st) : launch<64, 6, 8, false>(ma, mb, mc, mx, p, splits, st);
   if (BN == 192) return aux_epi ? launch<192, 3, 12, true>(ma, mb, mc, mx, p, splits, st) : launch<192, 4, 12, false>(ma, mb, mc, mx, p, splits, st);
   return aux_epi ? launch<128, 4, 16, true>(ma, mb, mc, mx, p, splits, st) : launch<128, 4, 16, false>(ma, mb, mc, mx, p, splits, st);
 }
 
 int apb_gemm_tc_rowsum_slots(int N, int split_k) {
-  const int bn = (ceil_div(N, 192) * 192 <= ceil_div(N, 128) * 128) ? 192 : 128;
-  return (split_k < 1 ? 1 : split_k) * ceil_div(N, bn);
+  return (split_k < 1 ? 1 : split_k) * ceil_div(N, pick_bn(N));
 }
 
 int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* aux, int M, int N, int K, int trans_a,
@@ -590,8 +606,7 @@ int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* 
 
 // number of K splits the wgrad-shaped GEMM should use to fill the GPU (host helper for the binding)
 int apb_gemm_tc_suggest_split(int M, int N, int K) {
-  const int bn = (ceil_div(N, 192) * 192 <= ceil_div(N, 128) * 128) ? 192 : 128;
-  const int tiles = ceil_div(M, BM) * ceil_div(N, bn);
+  const int tiles = ceil_div(M, BM) * ceil_div(N, pick_bn(N));
   const int total_kb = (K + BK - 1) / BK;
   const int sms = 148;
   if (tiles >= sms || total_kb < 16) return 1;

@@ -268,6 +268,18 @@ def unpatchify(rows, B: int, H: int, W: int, Cc: int, p: int):
     return x
 
 
+def im2col(x, KH: int, KW: int, stride: int, pad: int, Kpad: int):
+    """x: [B, C, H, W] (any strides, fp32 / bf16) -> bf16 [B*OH*OW, Kpad], column k = c*KH*KW + ky*KW + kx."""
+    B, Cc, H, W = x.shape
+    OH, OW = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    col = torch.empty((B * OH * OW, Kpad), device=x.device, dtype=torch.bfloat16)
+    sb, sc, sh, sw = x.stride()
+    if not x.is_cuda:
+        raise RuntimeError('autoprog_b200 kernels need CUDA tensors (there is no CPU fallback)')
+    check(lib().apb_im2col(x.data_ptr(), _p(col), B, Cc, H, W, KH, KW, stride, pad, Kpad, sb, sc, sh, sw, dt(x), _st()), 'im2col')
+    return col, OH, OW
+
+
 def bicubic_resize(src, h0: int, w0: int):
     h, w, Cc = src.shape
     dst = torch.empty((h0, w0, Cc), device=src.device, dtype=torch.float32)

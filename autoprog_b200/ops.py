@@ -342,6 +342,48 @@ def wcast_conv(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return w2
 
 
+def wcast_conv_kpad(weight: torch.Tensor, Kpad: int) -> torch.Tensor:
+    """[Cout,Cin,KH,KW] conv weight -> cached bf16 [Cout, Kpad] GEMM weight, K order (cin,kh,kw), zero-padded columns."""
+    key = (id(weight), Kpad)
+    ent = _CONVW.get(key)
+    if ent is not None and ent[0] == weight._version and ent[1] == weight.data_ptr():
+        return ent[2]
+    co = weight.shape[0]
+    w2 = torch.zeros((co, Kpad), device=weight.device, dtype=BF16)
+    w2[:, :weight[0].numel()] = weight.detach().reshape(co, -1)
+    if ent is None:
+        weakref.finalize(weight, _CONVW.pop, key, None)
+    _CONVW[key] = (weight._version, weight.data_ptr(), w2, BF16)
+    return w2
+
+
+class StemConvFn(torch.autograd.Function):
+    """The 7x7 stride-2 stem convolution (Cin = 3; models/volo.py:352-353) in bf16 mode: im2col kernel + one tcgen05
+    GEMM; weight gradient = one split-K GEMM over the saved im2col rows.  NCHW (any strides) in, NHWC bf16 out.
+    The image itself gets no gradient through this path (callers that need d/dx use the library convolution)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad):
+        co, ci, kh, kw = weight.shape
+        kpad = (ci * kh * kw + 7) // 8 * 8
+        col, OH, OW = K.im2col(x, kh, kw, stride, pad, kpad)
+        w2 = wcast_conv_kpad(weight, kpad)
+        y = K.gemm(col, w2, col.shape[0], co, kpad)
+        ctx.save_for_backward(col)
+        ctx.meta = (tuple(weight.shape), kpad)
+        return y.reshape(x.shape[0], OH, OW, co)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (col,) = ctx.saved_tensors
+        wshape, kpad = ctx.meta
+        co = wshape[0]
+        dy2 = K.cast(_c(dy), BF16).reshape(-1, co)
+        dw2 = K.gemm(dy2, col, co, kpad, col.shape[0], trans_a=True, trans_b=True, out_dtype=F32)
+        dw = dw2[:, :wshape[1] * wshape[2] * wshape[3]].reshape(wshape)
+        return None, dw, None, None
+
+
 class PosEmbedAddFn(torch.autograd.Function):
     """x + bicubic_resize(pos_embed) (models/volo.py:580-596, 627-628); output joins the fp32 residual stream."""
 

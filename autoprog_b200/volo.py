@@ -304,8 +304,9 @@ def rand_bbox(size, lam, scale=1):
 
 
 class PatchEmbed(nn.Module):
-    """models/volo.py:342-380.  The 7x7/3x3 stem convs + BatchNorm + ReLU run through cuDNN/ATen (library: not one of
-    the north-star kernels); the patch projection conv (kernel == stride) is patchify + our GEMM."""
+    """models/volo.py:342-380.  bf16 mode: the 7x7 RGB stem conv is im2col + our tcgen05 GEMM (ops.StemConvFn), the two
+    3x3 64->64 convs run through cuDNN (library implicit GEMM), BatchNorm+ReLU is our fused kernel, and the patch
+    projection conv (kernel == stride) is patchify + our GEMM.  fp32 parity mode: all three stem convs via cuDNN."""
 
     def __init__(self, img_size=224, stem_conv=False, stem_stride=1, patch_size=8, in_chans=3, hidden_dim=64,
                  embed_dim=384):
@@ -333,24 +334,31 @@ class PatchEmbed(nn.Module):
                     and isinstance(mods[i + 2], nn.ReLU) and K.bn_supported(mods[i + 1].num_features)
                     and mods[i + 1].affine and mods[i + 1].track_running_stats and mods[i + 1].momentum is not None)
             if not fuse:
-                x = m(x)
+                x = m(x.contiguous(memory_format=torch.channels_last) if isinstance(m, nn.Conv2d) else x)
                 i += 1
                 continue
             bn = mods[i + 1]
-            x = m(x)
+            nhwc = None
+            if (torch.is_autocast_enabled('cuda') and not x.requires_grad and m.bias is None and m.groups == 1
+                    and m.dilation == (1, 1) and m.in_channels <= 4 and m.stride[0] == m.stride[1]
+                    and m.padding[0] == m.padding[1] and isinstance(m.padding[0], int)
+                    and K.tc_supported(8, m.out_channels, 8)):
+                # few input channels (the 7x7 stem conv on RGB): im2col + tcgen05 GEMM instead of the library conv
+                nhwc = ops.StemConvFn.apply(x, m.weight, m.stride[0], m.padding[0])
+            else:
+                x = m(x.contiguous(memory_format=torch.channels_last))
             use_batch = bn.training
             if use_batch:
                 with torch.no_grad():
                     bn.num_batches_tracked += 1
-            y = ops.BNReLUFn.apply(x.permute(0, 2, 3, 1), bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                   float(bn.momentum), float(bn.eps), use_batch)
+            y = ops.BNReLUFn.apply(nhwc if nhwc is not None else x.permute(0, 2, 3, 1), bn.weight, bn.bias,
+                                   bn.running_mean, bn.running_var, float(bn.momentum), float(bn.eps), use_batch)
             x = y.permute(0, 3, 1, 2)
             i += 3
         return x
 
     def forward_nhwc(self, x):
         if self.stem_conv:
-            x = x.contiguous(memory_format=torch.channels_last)
             if torch.is_autocast_enabled('cuda'):
                 x = self._stem(x)
             else:   # fp32 parity mode: keep cuDNN off TF32

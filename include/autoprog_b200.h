@@ -142,6 +142,12 @@ int apb_flip_in_box_dev(const void* x, void* y, int B, int H, int W, int C, cons
                         apb_stream_t stream);   /* box (r0,c0,r1,c1) * box_scale read from device memory */
 int apb_patchify(const void* x, void* rows, int B, int H, int W, int C, int p, int dtype, apb_stream_t stream);
 int apb_unpatchify(const void* rows, void* x, int B, int H, int W, int C, int p, int dtype, apb_stream_t stream);
+/* im2col of a small-channel convolution input (the 7x7 stride-2 stem conv of PatchEmbed, models/volo.py:352-353):
+ * col [B*OH*OW, Kpad] bf16, column k = c*KH*KW + ky*KW + kx (== the row layout of the nn.Conv2d weight), zero-padded to
+ * Kpad (multiple of 8) and outside the image.  x is read through element strides (sb, sc, sh, sw): NCHW or NHWC,
+ * fp32 or bf16.  The conv itself is then one tcgen05 GEMM (apb_gemm_tc) and its weight gradient another. */
+int apb_im2col(const void* x, void* col, int B, int C, int H, int W, int KH, int KW, int stride, int pad, int Kpad,
+               long long sb, long long sc, long long sh, long long sw, int in_dtype, apb_stream_t stream);
 int apb_bicubic_resize(const float* src, float* dst, int h, int w, int h0, int w0, int C, apb_stream_t stream);
 int apb_bicubic_resize_bwd(const float* ddst, float* dsrc, int h, int w, int h0, int w0, int C, apb_stream_t stream);
 int apb_add_bcast(const void* x, const float* p, void* out, long long batch, long long inner, int in_dtype,

@@ -437,3 +437,31 @@ def test_batchnorm_relu_fused(rows, C, dtype):
     bn.eval()
     ye, _, _ = K.bn_relu_fwd(x.to(dev, dtype), g.to(dev), b.to(dev), rmd, rvd, 0.1, 1e-5, False)
     assert rel(ye, torch.relu(bn(x))) < t
+
+
+@pytest.mark.parametrize('shape', [(2, 3, 64, 64, 16, 7, 2, 3), (1, 3, 65, 47, 64, 7, 2, 3), (3, 1, 32, 40, 8, 3, 1, 1),
+                                   (2, 4, 30, 30, 24, 5, 3, 2)])
+@pytest.mark.parametrize('layout', ['nchw', 'nhwc'])
+def test_stem_conv_im2col_gemm(shape, layout):
+    """StemConvFn (im2col kernel + tcgen05 GEMM, wgrad GEMM) == conv2d in fp64 on the same bf16-rounded operands."""
+    import torch.nn.functional as F
+    from autoprog_b200 import ops
+    dev = need_gpu()
+    B, Ci, H, W, Co, k, stride, pad = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(B, Ci, H, W)
+    w = (torch.randn(Co, Ci, k, k) * 0.1)
+    xq, wq = x.to(torch.bfloat16).double(), w.to(torch.bfloat16).double()
+    wref = wq.clone().requires_grad_(True)
+    y_ref = F.conv2d(xq, wref, stride=stride, padding=pad)
+    dy = torch.randn_like(y_ref).to(torch.bfloat16).double()
+    y_ref.backward(dy)
+    xd = x.to(dev)
+    if layout == 'nhwc':
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    wd = w.to(dev).requires_grad_(True)
+    y = ops.StemConvFn.apply(xd, wd, stride, pad)                  # NHWC bf16
+    assert y.shape == (B, y_ref.shape[2], y_ref.shape[3], Co)
+    assert rel(y.permute(0, 3, 1, 2), y_ref) < 2e-2
+    y.backward(dy.permute(0, 2, 3, 1).to(dev, torch.bfloat16).contiguous())
+    assert rel(wd.grad, wref.grad) < 2e-2, rel(wd.grad, wref.grad)

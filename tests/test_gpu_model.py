@@ -46,6 +46,32 @@ def run_case(m, c, dev, bf16, seed):
 SEEDS = {'train_r64': 11, 'train_r96_bicubic': 12, 'train_r104_oddgrid': 13, 'eval_r80': 14, 'train_r64_elastic_dp': 21}
 
 
+@pytest.mark.parametrize('case', ['train_r64', 'train_r104_oddgrid'])
+def test_volo_small_golden_bf16_training_path(case):
+    """bf16 with an input that needs no gradient -- what training does: the 7x7 stem conv runs as im2col + tcgen05 GEMM."""
+    dev = need_gpu()
+    fx = torch.load(os.path.join(G, 'volo_small.pt'))
+    m = build(fx, dev)
+    c = fx['cases'][case]
+    np.random.seed(SEEDS[case])
+    m.train(True)
+    m.zero_grad(set_to_none=True)
+    with A.autocast(enabled=True):
+        out = m(c['x'].to(dev))
+        crit = A.TokenLabelCrossEntropy(dense_weight=c['dense_weight'], cls_weight=1.0, classes=12)
+        loss = crit(out, c['target'].to(dev))
+    loss.backward()
+    assert abs(float(loss) - float(c['loss'])) < 2e-2 * abs(float(c['loss']))
+    g = dict(m.named_parameters())['patch_embed.conv.0.weight'].grad
+    # per-tensor bound of the bf16 golden test (8 x 2e-2): the first layer's gradient carries the whole net's bf16 noise
+    assert g is not None and rel(g, c['grads']['patch_embed.conv.0.weight']) < 0.16, rel(g, c['grads']['patch_embed.conv.0.weight'])
+    both = [(p.grad.double().cpu(), c['grads'][n].double()) for n, p in m.named_parameters()
+            if p.grad is not None and c['grads'].get(n) is not None]
+    num = sum(float((a - b).pow(2).sum()) for a, b in both)
+    den = sum(float(b.pow(2).sum()) for a, b in both)
+    assert (num / den) ** 0.5 < 2e-2, (num / den) ** 0.5
+
+
 @pytest.mark.parametrize('bf16', [False, True])
 @pytest.mark.parametrize('case', ['train_r64', 'train_r96_bicubic', 'train_r104_oddgrid', 'eval_r80'])
 def test_volo_small_golden(case, bf16):
