@@ -11,6 +11,7 @@
 //         (3) dK,dV : CTA per (b, head), warp per 16 keys, Q/dO in smem.  No atomics -> deterministic.
 // Layouts: qkv [B,N,3,heads,32], out/dout [B,N,heads,32], lse/D [B,heads,N] fp32.
 #include "common.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -111,8 +112,8 @@ __device__ __forceinline__ void mma_rows(float (&o)[D / 8][4], const uint32_t (&
   }
 }
 
-template <int D>
-__global__ void __launch_bounds__(256, (D == 32 ? 3 : 1)) mhsa_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
+template <int D, int MINB>
+__global__ void __launch_bounds__(256, MINB) mhsa_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
                                                            float* __restrict__ lse, int N, int heads, float scale,
                                                            int rows_pad) {
   constexpr int ROWP = D + 8;
@@ -140,27 +141,33 @@ __global__ void __launch_bounds__(256, (D == 32 ? 3 : 1)) mhsa_fwd_mma_kernel(co
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
-    for (int kb = 0; kb * 64 < N; ++kb) {
-      const int k0 = kb * 64;
-      const bool tail = kb >= nfull;        // warp-uniform
+    // one 64-key block: S = Q K^T (registers), online softmax, O += P V.  TAIL = false: all 64 keys valid, no
+    // predicates anywhere (the steady state).  TAIL = true: only the first `nbv` 8-key sub-blocks exist; everything
+    // beyond them is skipped (warp-uniform), keys >= N inside the last sub-block are masked.
+    auto block = [&](auto tail_tag, const int k0) {
+      constexpr bool TAIL = decltype(tail_tag)::value;
+      const int nbv = TAIL ? (N - k0 + 7) >> 3 : 8;
       float s[8][4];
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
-        s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
-        if (!tail || k0 + nb * 8 < N) mma_rowsT<D>(s[nb], qa, sK_T + (uint32_t)(k0 + nb * 8) * ROWB);
-      }
-      if (tail) {
+        s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = TAIL ? -INFINITY : 0.f;
+        if (!TAIL || nb < nbv) {
+          s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+          mma_rowsT<D>(s[nb], qa, sK_T + (uint32_t)(k0 + nb * 8) * ROWB);
+          if (TAIL) {
 #pragma unroll
-        for (int nb = 0; nb < 8; ++nb)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (k0 + nb * 8 + 2 * q + (j & 1) >= N) s[nb][j] = -INFINITY;
+            for (int j = 0; j < 4; ++j)
+              if (k0 + nb * 8 + 2 * q + (j & 1) >= N) s[nb][j] = -INFINITY;
+          }
+        }
       }
       float mt[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb)
+        if (!TAIL || nb < nbv) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mt[j >> 1] = fmaxf(mt[j >> 1], s[nb][j]);
+          for (int j = 0; j < 4; ++j) mt[j >> 1] = fmaxf(mt[j >> 1], s[nb][j]);
+        }
       float corr[2], msc[2];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -174,21 +181,27 @@ __global__ void __launch_bounds__(256, (D == 32 ? 3 : 1)) mhsa_fwd_mma_kernel(co
       for (int i = 0; i < D / 8; ++i) { o[i][0] *= corr[0]; o[i][1] *= corr[0]; o[i][2] *= corr[1]; o[i][3] *= corr[1]; }
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb)
+        if (!TAIL || nb < nbv) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float pv = ex2(fmaf(s[nb][j], sl2, -msc[j >> 1]));
-          s[nb][j] = pv;
-          l_run[j >> 1] += pv;
+          for (int j = 0; j < 4; ++j) {
+            const float pv = ex2(fmaf(s[nb][j], sl2, -msc[j >> 1]));
+            s[nb][j] = pv;
+            l_run[j >> 1] += pv;
+          }
+        } else {
+          s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
         }
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        if (!tail || k0 + kk * 16 < N) {
+        if (!TAIL || 2 * kk < nbv) {
           const uint32_t pa[4] = {pack_bf16(s[2 * kk][0], s[2 * kk][1]), pack_bf16(s[2 * kk][2], s[2 * kk][3]),
                                   pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3])};
           mma_rows<D>(o, pa, sV_R + (uint32_t)(k0 + kk * 16) * ROWB);
         }
       }
-    }
+    };
+    for (int kb = 0; kb < nfull; ++kb) block(std::false_type{}, kb * 64);
+    if (nfull * 64 < N) block(std::true_type{}, nfull * 64);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const float l = quad_sum(l_run[h]);
@@ -235,8 +248,8 @@ __global__ void __launch_bounds__(256) mhsa_rowdot_kernel(const bf16* __restrict
 }
 
 // dQ: warp per 16 queries; S = Q K^T, P = exp(S*scale - lse), dP = dO V^T, dS = P*(dP - D), dQ = scale * dS K
-template <int D>
-__global__ void __launch_bounds__(256, (D == 32 ? 3 : 1)) mhsa_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
+template <int D, int MINB>
+__global__ void __launch_bounds__(256, MINB) mhsa_bwd_dq_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
                                                               const float* __restrict__ lse, const float* __restrict__ drow,
                                                               bf16* __restrict__ dqkv, int N, int heads, float scale,
                                                               int rows_pad) {
@@ -274,7 +287,8 @@ __global__ void __launch_bounds__(256, (D == 32 ? 3 : 1)) mhsa_bwd_dq_mma_kernel
     for (int i = 0; i < D / 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
-    for (int k0 = 0; k0 < N; k0 += 16) {
+    auto step = [&](auto tail_tag, const int k0) {
+      constexpr bool TAIL = decltype(tail_tag)::value;
       float s[2][4], dp[2][4];
 #pragma unroll
       for (int nb = 0; nb < 2; ++nb) {
@@ -284,15 +298,18 @@ __global__ void __launch_bounds__(256, (D == 32 ? 3 : 1)) mhsa_bwd_dq_mma_kernel
         mma_rowsT<D>(dp[nb], ga, sV_T + (uint32_t)(k0 + nb * 8) * ROWB);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int key = k0 + nb * 8 + 2 * q + (j & 1);
-          const float pv = (key < N) ? ex2(s[nb][j] * sl2 - l2[j >> 1]) : 0.f;
+          float pv = ex2(fmaf(s[nb][j], sl2, -l2[j >> 1]));
+          if (TAIL && k0 + nb * 8 + 2 * q + (j & 1) >= N) pv = 0.f;
           s[nb][j] = pv * (dp[nb][j] - dr[j >> 1]);
         }
       }
-      uint32_t pa[4] = {pack_bf16(s[0][0], s[0][1]), pack_bf16(s[0][2], s[0][3]), pack_bf16(s[1][0], s[1][1]),
-                        pack_bf16(s[1][2], s[1][3])};
+      const uint32_t pa[4] = {pack_bf16(s[0][0], s[0][1]), pack_bf16(s[0][2], s[0][3]), pack_bf16(s[1][0], s[1][1]),
+                              pack_bf16(s[1][2], s[1][3])};
       mma_rows<D>(dq, pa, sK_R + (uint32_t)k0 * ROWB);
-    }
+    };
+    const int kfull = N & ~15;
+    for (int k0 = 0; k0 < kfull; k0 += 16) step(std::false_type{}, k0);
+    if (kfull < N) step(std::true_type{}, kfull);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int r = row0 + gi + h * 8;
@@ -345,7 +362,8 @@ __global__ void __launch_bounds__(256, (D == 32 ? 2 : 1)) mhsa_bwd_dkv_mma_kerne
     for (int i = 0; i < D / 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) { dk[i][j] = 0.f; dv[i][j] = 0.f; }
-    for (int i0 = 0; i0 < N; i0 += 16) {
+    auto step = [&](auto tail_tag, const int i0) {
+      constexpr bool TAIL = decltype(tail_tag)::value;
       float s[2][4], dp[2][4];
       uint32_t pp[4], ds[4];
 #pragma unroll
@@ -354,12 +372,14 @@ __global__ void __launch_bounds__(256, (D == 32 ? 2 : 1)) mhsa_bwd_dkv_mma_kerne
         dp[nb][0] = dp[nb][1] = dp[nb][2] = dp[nb][3] = 0.f;
         mma_rowsT<D>(s[nb], ka, sQ_T + (uint32_t)(i0 + nb * 8) * ROWB);     // S^T[key][query]
         mma_rowsT<D>(dp[nb], va, sG_T + (uint32_t)(i0 + nb * 8) * ROWB);    // dP^T[key][query]
+        const int qi0 = i0 + nb * 8 + 2 * q;                                 // this lane's two queries: qi0, qi0 + 1
+        const float2 lq = *reinterpret_cast<const float2*>(sL + qi0), dq2 = *reinterpret_cast<const float2*>(sD + qi0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int qi = i0 + nb * 8 + 2 * q + (j & 1);
-          const float pv = (qi < N) ? ex2(s[nb][j] * sl2 - sL[qi]) : 0.f;
+          float pv = ex2(fmaf(s[nb][j], sl2, -((j & 1) ? lq.y : lq.x)));
+          if (TAIL && qi0 + (j & 1) >= N) pv = 0.f;
           s[nb][j] = pv;
-          dp[nb][j] = pv * (dp[nb][j] - sD[qi]);
+          dp[nb][j] = pv * (dp[nb][j] - ((j & 1) ? dq2.y : dq2.x));
         }
         pp[nb * 2 + 0] = pack_bf16(s[nb][0], s[nb][1]);
         pp[nb * 2 + 1] = pack_bf16(s[nb][2], s[nb][3]);
@@ -368,7 +388,10 @@ __global__ void __launch_bounds__(256, (D == 32 ? 2 : 1)) mhsa_bwd_dkv_mma_kerne
       }
       mma_rows<D>(dv, pp, sG_R + (uint32_t)i0 * ROWB);
       mma_rows<D>(dk, ds, sQ_R + (uint32_t)i0 * ROWB);
-    }
+    };
+    const int ifull = N & ~15;
+    for (int i0 = 0; i0 < ifull; i0 += 16) step(std::false_type{}, i0);
+    if (ifull < N) step(std::true_type{}, ifull);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int r = key0 + gi + h * 8;
@@ -399,8 +422,10 @@ static int mhsa_fwd_mma_t(const void* qkv, void* out, float* lse, int B, int N, 
   const int rows_pad = (N + 63) / 64 * 64;
   const size_t smem = (size_t)2 * rows_pad * ROWP * sizeof(bf16);
   APB_CHECK_ARG(smem <= 227 * 1024, APB_ERR_UNSUPPORTED, "mhsa_fwd_mma: N=%d needs %zu B smem", N, smem);
-  cudaFuncSetAttribute(mhsa_fwd_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  mhsa_fwd_mma_kernel<D><<<B * heads, pick_warps(N) * 32, smem, st>>>((const bf16*)qkv, (bf16*)out, lse, N, heads, scale, rows_pad);
+  // D = 32: 3 CTAs / SM (80-register cap, a few spilled bytes) measured faster than 2 CTAs without spills (75 vs 86 us)
+  constexpr int MINB = (D == 32) ? 3 : 1;
+  cudaFuncSetAttribute(mhsa_fwd_mma_kernel<D, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mhsa_fwd_mma_kernel<D, MINB><<<B * heads, pick_warps(N) * 32, smem, st>>>((const bf16*)qkv, (bf16*)out, lse, N, heads, scale, rows_pad);
   APB_LAUNCH_CHECK("mhsa_fwd_mma");
   return 0;
 }
@@ -416,11 +441,12 @@ static int mhsa_bwd_mma_t(const void* qkv, const void* out, const void* dout, co
   const long long total = (long long)B * N * heads;
   mhsa_rowdot_kernel<D><<<ceil_div(total, 256), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, workspace, B, N, heads);
   APB_LAUNCH_CHECK("mhsa_rowdot");
-  cudaFuncSetAttribute(mhsa_bwd_dq_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+  constexpr int MINB = (D == 32) ? 3 : 1;
+  cudaFuncSetAttribute(mhsa_bwd_dq_mma_kernel<D, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
   cudaFuncSetAttribute(mhsa_bwd_dkv_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
   const int threads = pick_warps(N) * 32;
-  mhsa_bwd_dq_mma_kernel<D><<<B * heads, threads, smem1, st>>>((const bf16*)qkv, (const bf16*)dout, lse, workspace, (bf16*)dqkv,
-                                                              N, heads, scale, rows_pad);
+  mhsa_bwd_dq_mma_kernel<D, MINB><<<B * heads, threads, smem1, st>>>((const bf16*)qkv, (const bf16*)dout, lse, workspace, (bf16*)dqkv,
+                                                                    N, heads, scale, rows_pad);
   APB_LAUNCH_CHECK("mhsa_bwd_dq_mma");
   mhsa_bwd_dkv_mma_kernel<D><<<B * heads, threads, smem2, st>>>((const bf16*)qkv, (const bf16*)dout, lse, workspace, (bf16*)dqkv,
                                                                N, heads, scale, rows_pad);
