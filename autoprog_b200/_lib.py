@@ -48,6 +48,7 @@ SIGNATURES = {
     'apb_patchify': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'apb_unpatchify': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     'apb_im2col': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _vp]),
+    'apb_bilinear_resize': (_i, [_vp, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     'apb_bicubic_resize': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'apb_bicubic_resize_bwd': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     'apb_add_bcast': (_i, [_vp, _vp, _vp, _ll, _ll, _i, _i, _vp]),

@@ -248,6 +248,27 @@ __global__ void gelu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ d
 }
 
 
+// Input resolution switch of the progressive schedule (main_prog.py:973-974, 1910): F.interpolate(x, size=(r, r),
+// mode='bilinear', align_corners=False) on an NCHW batch.  ATen semantics: src = max((dst + 0.5) * in/out - 0.5, 0),
+// i0 = floor(src), i1 = min(i0 + 1, in - 1), weights (1 - l, l).  One thread per output pixel, all planes of the image
+// share the index / weight computation via the grid's y dimension (plane = b * C + c).  Output fp32 or bf16.
+template <typename TO>
+__global__ void __launch_bounds__(EW_THREADS) bilinear_resize_kernel(const float* __restrict__ src, TO* __restrict__ dst, int H,
+                                                                     int W, int OH, int OW, float sy, float sx) {
+  const float* sp = src + (size_t)blockIdx.y * H * W;
+  TO* dp = dst + (size_t)blockIdx.y * OH * OW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < OH * OW; i += gridDim.x * blockDim.x) {
+    const int oy = i / OW, ox = i - oy * OW;
+    const float fy = fmaxf(((float)oy + 0.5f) * sy - 0.5f, 0.f), fx = fmaxf(((float)ox + 0.5f) * sx - 0.5f, 0.f);
+    const int y0 = min((int)fy, H - 1), x0 = min((int)fx, W - 1);
+    const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float v = hy * (hx * sp[y0 * W + x0] + lx * sp[y0 * W + x1]) + ly * (hx * sp[y1 * W + x0] + lx * sp[y1 * W + x1]);
+    dp[i] = from_f<TO>(v);
+  }
+}
+
 // im2col for a small-channel convolution (the 7x7 / stride-2 stem conv, models/volo.py:352): row = output pixel
 // (b, oy, ox), column k = c * KH * KW + ky * KW + kx (the memory order of an nn.Conv2d weight row), zero beyond
 // C * KH * KW (columns are padded to a multiple of 8 for the TMA row pitch) and for taps outside the image.
@@ -555,5 +576,25 @@ int apb_im2col(const void* x, void* col, int B, int C, int H, int W, int KH, int
                                                        sb, sc, sh, sw);
   } else { apb_set_error("im2col: unsupported dtype %d", in_dtype); return APB_ERR_DTYPE; }
   APB_LAUNCH_CHECK("im2col");
+  return 0;
+}
+
+int apb_bilinear_resize(const float* src, void* dst, long long planes, int H, int W, int OH, int OW, int out_dtype,
+                        apb_stream_t stream) {
+  cudaStream_t st = APB_STREAM(stream);
+  APB_CHECK_ARG(planes > 0 && planes <= 65535LL * 1024 && H > 0 && W > 0 && OH > 0 && OW > 0, APB_ERR_SHAPE, "bilinear_resize: bad shape");
+  const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+  int gx = ceil_div(OH * OW, EW_THREADS);
+  if (gx > 64) gx = 64;
+  for (long long p0 = 0; p0 < planes; p0 += 65535) {     // grid.y limit
+    const int np = (int)((planes - p0 < 65535) ? planes - p0 : 65535);
+    const float* s = src + (size_t)p0 * H * W;
+    if (out_dtype == APB_F32)
+      bilinear_resize_kernel<float><<<dim3(gx, np), EW_THREADS, 0, st>>>(s, (float*)dst + (size_t)p0 * OH * OW, H, W, OH, OW, sy, sx);
+    else if (out_dtype == APB_BF16)
+      bilinear_resize_kernel<bf16><<<dim3(gx, np), EW_THREADS, 0, st>>>(s, (bf16*)dst + (size_t)p0 * OH * OW, H, W, OH, OW, sy, sx);
+    else { apb_set_error("bilinear_resize: unsupported out dtype %d", out_dtype); return APB_ERR_DTYPE; }
+    APB_LAUNCH_CHECK("bilinear_resize");
+  }
   return 0;
 }

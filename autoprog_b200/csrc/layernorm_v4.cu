@@ -230,19 +230,41 @@ __global__ void __launch_bounds__(256) colsum_v8_kernel(const T* __restrict__ a,
 
 // out[i] = sum_s parts[s][i] (fixed order): the deterministic tail of the split-K wgrad GEMM, one launch.  A second,
 // small job (the bias-gradient partials of the same GEMM) rides along in the same grid.
+// block = 64 float4 columns x 4 split phases: phase g sums the splits s = g, g+4, ... (two loads in flight), the four
+// phase sums are then added in fixed order through shared memory -- the partials are a few MB spread over 8-63
+// splits, so parallelism over the split dimension is what keeps the loads in flight.
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ parts, float* __restrict__ out, int splits,
                                                             long long n4, const float* __restrict__ parts2,
                                                             float* __restrict__ out2, long long n4b, int splits2) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + n4b; i += (long long)gridDim.x * blockDim.x) {
-    const bool second = i >= n4;
-    const float4* src = reinterpret_cast<const float4*>(second ? parts2 : parts);
-    const long long j = second ? i - n4 : i, stride = second ? n4b : n4;
-    float4 acc = src[j];
-    const int ns = second ? splits2 : splits;
-    for (int s = 1; s < ns; ++s) {
-      const float4 v = src[(long long)s * stride + j];
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  __shared__ float4 sm[4][64];
+  const int tx = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const long long i = (long long)blockIdx.x * 64 + tx;
+  const bool live = i < n4 + n4b;
+  const bool second = i >= n4;
+  const float4* src = reinterpret_cast<const float4*>(second ? parts2 : parts);
+  const long long j = second ? i - n4 : i, stride = second ? n4b : n4;
+  const int ns = second ? splits2 : splits;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    int s = g;
+    for (; s + 4 < ns; s += 8) {
+      const float4 a = src[(long long)s * stride + j], b = src[(long long)(s + 4) * stride + j];
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
     }
+    if (s < ns) {
+      const float4 a = src[(long long)s * stride + j];
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  }
+  sm[g][tx] = acc;
+  __syncthreads();
+  if (g == 0 && live) {
+    const float4 b = sm[1][tx], c = sm[2][tx], d = sm[3][tx];
+    acc.x = ((acc.x + b.x) + c.x) + d.x;
+    acc.y = ((acc.y + b.y) + c.y) + d.y;
+    acc.z = ((acc.z + b.z) + c.z) + d.z;
+    acc.w = ((acc.w + b.w) + c.w) + d.w;
     reinterpret_cast<float4*>(second ? out2 : out)[j] = acc;
   }
 }
@@ -257,8 +279,8 @@ int apb_splitk_reduce2(const float* parts, float* out, long long n, int splits, 
   APB_CHECK_ARG(n2 == 0 || (parts2 != nullptr && out2 != nullptr && (n2 % 4) == 0 && (((uintptr_t)parts2 | (uintptr_t)out2) & 15) == 0),
                 APB_ERR_ARG, "splitk_reduce: second job n2=%lld must be a multiple of 4 with 16-byte aligned pointers", n2);
   const long long n4 = n / 4, n4b = n2 / 4;
-  long long grid = (n4 + n4b + 255) / 256;
-  if (grid > 148 * 8) grid = 148 * 8;
+  const long long grid = (n4 + n4b + 63) / 64;
+  APB_CHECK_ARG(grid <= 0x7fffffffLL, APB_ERR_SHAPE, "splitk_reduce: n too large");
   splitk_reduce_kernel<<<(int)grid, 256, 0, st>>>(parts, out, splits, n4, parts2, out2, n4b, splits2 < 1 ? 1 : splits2);
   APB_LAUNCH_CHECK("splitk_reduce");
   return 0;

@@ -280,6 +280,16 @@ def im2col(x, KH: int, KW: int, stride: int, pad: int, Kpad: int):
     return col, OH, OW
 
 
+def bilinear_resize(x: torch.Tensor, OH: int, OW: int, out_dtype=None) -> torch.Tensor:
+    """[B, C, H, W] fp32 -> [B, C, OH, OW] (fp32 or bf16): F.interpolate(mode='bilinear', align_corners=False)."""
+    B, Cc, H, W = x.shape
+    assert x.dtype == torch.float32, x.dtype
+    out_dtype = out_dtype or x.dtype
+    out = torch.empty((B, Cc, OH, OW), device=x.device, dtype=out_dtype)
+    check(lib().apb_bilinear_resize(_p(x), _p(out), B * Cc, H, W, OH, OW, _CODES[out_dtype], _st()), 'bilinear_resize')
+    return out
+
+
 def bicubic_resize(src, h0: int, w0: int):
     h, w, Cc = src.shape
     dst = torch.empty((h0, w0, Cc), device=src.device, dtype=torch.float32)

@@ -34,3 +34,13 @@ def progressive_schedule(args, r_max=224, h_max=12, l_max=18):
     hi = _ramp(args.resize_scale[1], n) * args.scale[1]
     crop = [[max(0., a), max(0., b)] for a, b in zip(lo, hi)]
     return epochs, res, heads, depth, aug, drop_path, erase, crop
+
+
+def resize_input(x, r: int, out_dtype=None):
+    """The per-step resolution switch of the trainer (main_prog.py:973-974 and :1910):
+    `F.interpolate(input, size=(r, r), mode='bilinear', align_corners=False)` as one kernel; identity when the batch
+    already has resolution r.  x: [B, C, H, W] fp32 on the GPU."""
+    from . import kernels as K
+    if x.shape[-2] == r and x.shape[-1] == r and (out_dtype is None or out_dtype == x.dtype):
+        return x
+    return K.bilinear_resize(x.contiguous(), r, r, out_dtype)

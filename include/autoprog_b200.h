@@ -148,6 +148,11 @@ int apb_unpatchify(const void* rows, void* x, int B, int H, int W, int C, int p,
  * fp32 or bf16.  The conv itself is then one tcgen05 GEMM (apb_gemm_tc) and its weight gradient another. */
 int apb_im2col(const void* x, void* col, int B, int C, int H, int W, int KH, int KW, int stride, int pad, int Kpad,
                long long sb, long long sc, long long sh, long long sw, int in_dtype, apb_stream_t stream);
+/* Input resolution switch of the progressive schedule: F.interpolate(x, size=(OH, OW), mode='bilinear',
+ * align_corners=False) (main_prog.py:973-974, 1910) on `planes` = B*C contiguous H x W fp32 planes (NCHW);
+ * dst fp32 or bf16. */
+int apb_bilinear_resize(const float* src, void* dst, long long planes, int H, int W, int OH, int OW, int out_dtype,
+                        apb_stream_t stream);
 int apb_bicubic_resize(const float* src, float* dst, int h, int w, int h0, int w0, int C, apb_stream_t stream);
 int apb_bicubic_resize_bwd(const float* ddst, float* dsrc, int h, int w, int h0, int w0, int C, apb_stream_t stream);
 int apb_add_bcast(const void* x, const float* p, void* out, long long batch, long long inner, int in_dtype,

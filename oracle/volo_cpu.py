@@ -279,6 +279,28 @@ def bicubic_matrix(n_in: int, n_out: int) -> Tensor:
     return M
 
 
+def bilinear_matrix(n_in: int, n_out: int) -> Tensor:
+    """[n_out, n_in] fp64 matrix of upsample_bilinear2d(align_corners=False, size=n_out): the input resolution switch
+    `F.interpolate(input, size=(r, r), mode='bilinear', align_corners=False)` (main_prog.py:973-974, 1910)."""
+    M = torch.zeros(n_out, n_in, dtype=torch.float64)
+    scale = n_in / n_out
+    for o in range(n_out):
+        src = max((o + 0.5) * scale - 0.5, 0.0)
+        i0 = min(int(math.floor(src)), n_in - 1)
+        i1 = min(i0 + 1, n_in - 1)
+        lam = src - i0
+        M[o, i0] += 1.0 - lam
+        M[o, i1] += lam
+    return M
+
+
+def resize_input(x: Tensor, r: int) -> Tensor:
+    """x [B,C,H,W] -> [B,C,r,r], the trainer's per-step bilinear resolution switch (main_prog.py:973-974)."""
+    My = bilinear_matrix(x.shape[2], r).to(x.dtype)
+    Mx = bilinear_matrix(x.shape[3], r).to(x.dtype)
+    return torch.einsum('yh,xw,bchw->bcyx', My, Mx, x)
+
+
 def pos_embed_resize(pos: Tensor, h0: int, w0: int) -> Tensor:
     """VOLO.interpolate_pos_encoding, models/volo.py:580-596: pos [1,h,w,C] -> [1,h0,w0,C] (identity if equal)."""
     _, h, w, C = pos.shape

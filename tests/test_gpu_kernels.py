@@ -465,3 +465,21 @@ def test_stem_conv_im2col_gemm(shape, layout):
     assert rel(y.permute(0, 3, 1, 2), y_ref) < 2e-2
     y.backward(dy.permute(0, 2, 3, 1).to(dev, torch.bfloat16).contiguous())
     assert rel(wd.grad, wref.grad) < 2e-2, rel(wd.grad, wref.grad)
+
+
+@pytest.mark.parametrize('shape', [(4, 3, 224, 224, 128), (2, 3, 224, 224, 160), (2, 3, 224, 224, 192), (1, 3, 37, 53, 20),
+                                   (1, 2, 20, 24, 57), (2, 3, 64, 64, 64)])
+def test_resize_input_bilinear(shape):
+    """the trainer's per-step resolution switch (main_prog.py:973-974): kernel == oracle, fp32 and bf16 output."""
+    from autoprog_b200.progressive import resize_input
+    dev = need_gpu()
+    B, C, H, W, r = shape
+    torch.manual_seed(sum(shape))
+    x = torch.randn(B, C, H, W)
+    ref = O.resize_input(x.double(), r)
+    y = resize_input(x.to(dev), r)
+    # source coordinates are computed in fp32 like ATen's CUDA kernel (accscalar = float): for non-dyadic scales the
+    # interpolation weights carry ~1e-5 relative rounding against the fp64 oracle
+    assert y.shape == (B, C, r, r) and rel(y, ref) < 3e-5, rel(y, ref)
+    yb = resize_input(x.to(dev), r, torch.bfloat16)
+    assert yb.dtype == torch.bfloat16 and rel(yb, ref) < 5e-3

@@ -138,3 +138,15 @@ def test_losses():
     assert abs(float(O.soft_ce(fx['x_cls'], fx['t2']) - fx['cases']['soft']['loss'])) < 1e-12
     assert abs(float(O.soft_ce(fx['x_aux'].reshape(-1, C)[:8], fx['t2']) - fx['cases']['soft_rep']['loss'])) < 1e-12
     assert abs(float(O.soft_ce(fx['x_cls'], fx['t3'][:, :, 1]) - fx['cases']['tlsoft']['loss'])) < 1e-12
+
+
+def test_oracle_resize_input_matches_the_reference_call():
+    """main_prog.py:973-974 / :1910 call F.interpolate(input, size=(r, r), mode='bilinear', align_corners=False);
+    the oracle's separable-matrix restatement must equal that exact call (fp64)."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    for (H, W, r) in [(224, 224, 128), (224, 224, 160), (224, 224, 192), (224, 224, 224), (37, 53, 20), (20, 24, 57)]:
+        x = torch.randn(2, 3, H, W, dtype=torch.float64)
+        ref = F.interpolate(x, size=(r, r), mode='bilinear', align_corners=False)
+        got = O.resize_input(x, r)
+        assert float((got - ref).abs().max()) < 1e-12, (H, W, r)
