@@ -272,46 +272,65 @@ __global__ void __launch_bounds__(EW_THREADS) bilinear_resize_kernel(const float
 // im2col for a small-channel convolution (the 7x7 / stride-2 stem conv, models/volo.py:352): row = output pixel
 // (b, oy, ox), column k = c * KH * KW + ky * KW + kx (the memory order of an nn.Conv2d weight row), zero beyond
 // C * KH * KW (columns are padded to a multiple of 8 for the TMA row pitch) and for taps outside the image.
-// One CTA per output row (b, oy): the C * KH input rows it needs are staged ONCE in shared memory (coalesced reads,
-// zero-filled borders), then every thread gathers 8 consecutive columns and writes them as one 16-byte store.
-// The input is read through arbitrary element strides (NCHW or NHWC, fp32 or bf16).
+// One CTA per ROWS output rows of one image: the C * ((ROWS-1)*stride + KH) input rows it needs are staged ONCE in
+// shared memory (warp per row, coalesced, zero-filled borders); a per-CTA table maps column k to its offset in the
+// staged tile, so a thread produces 8 consecutive columns with one 16-byte table read + 8 gathers and writes them as
+// one 16-byte store.  The input is read through arbitrary element strides (NCHW or NHWC, fp32 or bf16).
+constexpr int IM2COL_ROWS = 4;
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_rows_kernel(const T* __restrict__ x, bf16* __restrict__ col, int C, int H, int W,
                                                           int KH, int KW, int stride, int pad, int OH, int OW, int Kpad,
-                                                          long long sb, long long sc, long long sh, long long sw) {
-  extern __shared__ float srow[];                       // [C * KH][SW], SW = W + 2 * pad
-  const int SW = W + 2 * pad;
-  const int b = blockIdx.x / OH, oy = blockIdx.x - b * OH;
-  const int iy0 = oy * stride - pad;
+                                                          long long sb, long long sc, long long sh, long long sw,
+                                                          unsigned inv_chunks) {
+  extern __shared__ __align__(16) unsigned char im2col_smem[];
+  const int SW = W + 2 * pad, IR = (IM2COL_ROWS - 1) * stride + KH;
+  short* lut = reinterpret_cast<short*>(im2col_smem);                      // [Kpad]
+  float* srow = reinterpret_cast<float*>(im2col_smem + ((Kpad * 2 + 15) & ~15));   // [C * IR][SW]
+  const int b = blockIdx.y, oy0 = blockIdx.x * IM2COL_ROWS;
+  const int Kreal = C * KH * KW;
+  for (int k = threadIdx.x; k < Kpad; k += 256) {
+    int off = -1;
+    if (k < Kreal) {
+      const int c = k / (KH * KW), r = k - c * KH * KW, ky = r / KW, kx = r - ky * KW;
+      off = (c * IR + ky) * SW + kx;
+    }
+    lut[k] = (short)off;
+  }
   const T* xb = x + (long long)b * sb;
-  const int nstage = C * KH * SW;
-  for (int e = threadIdx.x; e < nstage; e += 256) {
-    const int rr = e / SW, xx = e - rr * SW;            // rr = c * KH + ky
-    const int c = rr / KH, ky = rr - c * KH;
-    const int iy = iy0 + ky, ix = xx - pad;
-    float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = to_f(xb[c * sc + iy * sh + ix * sw]);
-    srow[e] = v;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int iy0 = oy0 * stride - pad;
+  for (int rr = warp; rr < C * IR; rr += 8) {
+    const int c = rr / IR, iy = iy0 + (rr - c * IR);
+    const bool yok = iy >= 0 && iy < H;
+    const T* g = xb + c * sc + (long long)(yok ? iy : 0) * sh;
+    float* d = srow + rr * SW;
+    for (int xx = lane; xx < SW; xx += 32) {
+      const int ix = xx - pad;
+      d[xx] = (yok && ix >= 0 && ix < W) ? to_f(g[ix * sw]) : 0.f;
+    }
   }
   __syncthreads();
-  const int chunks = Kpad >> 3, Kreal = C * KH * KW;
-  bf16* out = col + (size_t)blockIdx.x * OW * Kpad;
-  for (int e = threadIdx.x; e < OW * chunks; e += 256) {
-    const int ox = e / chunks, ch = e - ox * chunks;
-    const int k0 = ch * 8;
-    int rr = k0 / KW, kx = k0 - rr * KW;                // rr = c * KH + ky (rows of srow are in exactly this order)
-    const float* base = srow + ox * stride;
-    float v[8];
+  const int chunks = Kpad >> 3;
+  for (int orow = 0; orow < IM2COL_ROWS; ++orow) {
+    const int oy = oy0 + orow;
+    if (oy >= OH) break;
+    bf16* out = col + ((size_t)((size_t)b * OH + oy) * OW) * Kpad;
+    const float* rbase = srow + orow * stride * SW;
+    for (int e = threadIdx.x; e < OW * chunks; e += 256) {
+      const int ox = (int)__umulhi((unsigned)e, inv_chunks);               // e / chunks
+      const int ch = e - ox * chunks;
+      const uint4 lt = *reinterpret_cast<const uint4*>(lut + ch * 8);
+      const short* o8 = reinterpret_cast<const short*>(&lt);
+      const float* base = rbase + ox * stride;
+      float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] = (k0 + j < Kreal) ? base[rr * SW + kx] : 0.f;
-      if (++kx == KW) { kx = 0; ++rr; }
+      for (int j = 0; j < 8; ++j) v[j] = o8[j] >= 0 ? base[o8[j]] : 0.f;
+      uint4 pk;
+      __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      *reinterpret_cast<uint4*>(out + (size_t)e * 8) = pk;
     }
-    uint4 pk;
-    __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) h2[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-    *reinterpret_cast<uint4*>(out + (size_t)e * 8) = pk;
   }
 }
 
@@ -563,17 +582,22 @@ int apb_im2col(const void* x, void* col, int B, int C, int H, int W, int KH, int
   APB_CHECK_ARG(((uintptr_t)col & 15) == 0, APB_ERR_ARG, "im2col: col must be 16-byte aligned");
   const int OH = (H + 2 * pad - KH) / stride + 1, OW = (W + 2 * pad - KW) / stride + 1;
   APB_CHECK_ARG(OH > 0 && OW > 0, APB_ERR_SHAPE, "im2col: empty output");
-  const size_t smem = (size_t)C * KH * (W + 2 * pad) * sizeof(float);
-  APB_CHECK_ARG(smem <= 200 * 1024, APB_ERR_UNSUPPORTED, "im2col: C*KH*(W+2*pad) = %zu floats do not fit shared memory",
-                smem / sizeof(float));
+  const int SW = W + 2 * pad, IR = (IM2COL_ROWS - 1) * stride + KH;
+  const size_t smem = (size_t)((Kpad * 2 + 15) & ~15) + (size_t)C * IR * SW * sizeof(float);
+  APB_CHECK_ARG(smem <= 200 * 1024 && (long long)C * IR * SW < 32768, APB_ERR_UNSUPPORTED,
+                "im2col: staged tile of %d x %d floats does not fit (shared memory / 16-bit offsets)", C * IR, SW);
+  const int chunks = Kpad / 8;
+  APB_CHECK_ARG((long long)OW * chunks < 65536 && B <= 65535, APB_ERR_UNSUPPORTED, "im2col: row of %d x %d chunks too long", OW, chunks);
+  const unsigned inv_chunks = (unsigned)(0x100000000ULL / (unsigned)chunks) + 1u;   // exact for e < 65536
+  const dim3 grid(ceil_div(OH, IM2COL_ROWS), B);
   if (in_dtype == APB_F32) {
     cudaFuncSetAttribute(im2col_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    im2col_rows_kernel<float><<<B * OH, 256, smem, st>>>((const float*)x, (bf16*)col, C, H, W, KH, KW, stride, pad, OH, OW, Kpad,
-                                                        sb, sc, sh, sw);
+    im2col_rows_kernel<float><<<grid, 256, smem, st>>>((const float*)x, (bf16*)col, C, H, W, KH, KW, stride, pad, OH, OW, Kpad, sb,
+                                                      sc, sh, sw, inv_chunks);
   } else if (in_dtype == APB_BF16) {
     cudaFuncSetAttribute(im2col_rows_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    im2col_rows_kernel<bf16><<<B * OH, 256, smem, st>>>((const bf16*)x, (bf16*)col, C, H, W, KH, KW, stride, pad, OH, OW, Kpad,
-                                                       sb, sc, sh, sw);
+    im2col_rows_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)x, (bf16*)col, C, H, W, KH, KW, stride, pad, OH, OW, Kpad, sb,
+                                                     sc, sh, sw, inv_chunks);
   } else { apb_set_error("im2col: unsupported dtype %d", in_dtype); return APB_ERR_DTYPE; }
   APB_LAUNCH_CHECK("im2col");
   return 0;
