@@ -72,6 +72,13 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
@@ -181,7 +188,8 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + ACC_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + ACC_STAGES);
+  uint64_t* aux_bar = tempty_bar + ACC_STAGES;          // [EPI_WARPS][2]: gelu' tiles of the dGELU epilogue (AUX only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_bar + (AUX ? 2 * EPI_WARPS : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_kb = (p.K + BK - 1) / BK;
@@ -198,6 +206,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_x) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], EPI_WARPS); }
+    if (AUX) for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(&aux_bar[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -297,6 +306,26 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
     const int cg = (warp - 2) >> 2;               // which column slice of the tile
     uint8_t* stgC = stg_base + (warp - 2) * STG_BYTES;   // bf16: NCH boxes of 32 x 64 B; fp32: one 32 x 128 B box
     uint8_t* stgX = stgC + 4096;                         // aux boxes (bf16 32 x 64 B each)
+    // dGELU: the gelu'(pre-activation) sub-tiles of tile i+1 are fetched by TMA (same 32 x 32 / 64B-swizzle boxes the
+    // GELU forward stored them with) while tile i is in its epilogue.  Two box sets per warp, used alternately; the
+    // product is written IN PLACE over the gelu' box and TMA-stored from there, so no extra shared memory is needed.
+    uint64_t* my_aux_bar = aux_bar + (warp - 2) * 2;
+    auto prefetch_aux = [&](int item_, int set) {
+      if (lane != 0) return;
+      const int t_ = item_ / p.splits;
+      const int rb_ = (t_ / p.tiles_n) * BM + quarter * 32, cb_ = (t_ % p.tiles_n) * BN + cg * NCH * 32;
+      uint32_t bytes = 0;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if (rb_ < p.M && cb_ + c * 32 < p.N) bytes += 2048;
+      if (bytes == 0) { mbar_arrive(&my_aux_bar[set]); return; }       // keep the phases of the two sets in lockstep
+      mbar_expect_tx(&my_aux_bar[set], bytes);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if (cb_ + c * 32 < p.N) tma_load_3d((set ? stgX : stgC) + c * 2048, &tma_x, &my_aux_bar[set], cb_ + c * 32, rb_, 0);
+    };
+    const bool dgelu = AUX && p.epilogue == 2;
+    if (dgelu && (int)blockIdx.x < n_items) prefetch_aux(blockIdx.x, 0);
     uint32_t ai = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ai) {
       const int z = item % p.splits, t = item / p.splits;
@@ -304,22 +333,6 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       const uint32_t as = ai % ACC_STAGES;
       const int rb = m0 + quarter * 32;           // first row of this warp's sub-tile
       const int cb0 = n0 + cg * NCH * 32;         // first column
-      if (AUX && p.epilogue == 2 && rb < p.M) {
-        // dGELU: fetch the gelu'(pre-activation) sub-tiles (coalesced, 4 lanes per 64-byte row) while this tile's MMAs run
-        const bf16* ax = reinterpret_cast<const bf16*>(p.aux);
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int cb = cb0 + c * 32;
-          if (cb >= p.N) continue;
-#pragma unroll
-          for (int itr = 0; itr < 4; ++itr) {
-            const int rr = itr * 8 + (lane >> 2), ch = lane & 3;
-            uint4 val = make_uint4(0u, 0u, 0u, 0u);
-            if (rb + rr < p.M && cb + ch * 8 < p.N) val = *reinterpret_cast<const uint4*>(ax + (size_t)(rb + rr) * p.N + cb + ch * 8);
-            *reinterpret_cast<uint4*>(stg64(stgX + c * 2048, rr, ch)) = val;
-          }
-        }
-      }
       mbar_wait(&tfull_bar[as], (ai / ACC_STAGES) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t r[NCH][32];
@@ -340,6 +353,11 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous TMA stores have drained the staging boxes
       }
       __syncwarp();
+      if (dgelu) {
+        // the other box set is free (its TMA store was drained above): start fetching the next tile's gelu' now
+        if (item + (int)gridDim.x < n_items) prefetch_aux(item + gridDim.x, (ai & 1) ^ 1);
+        if (rb < p.M) mbar_wait(&my_aux_bar[ai & 1], (ai >> 1) & 1);
+      }
       if (rs_here && rb + lane < p.M) {
         const int tn = t % p.tiles_n;
         const int kb0 = z * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
@@ -351,7 +369,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
       for (int c = 0; c < NCH; ++c) {
         const int cb = cb0 + c * 32;
         if (cb >= p.N) continue;
-        uint8_t* sx = stgX + c * 2048;
+        uint8_t* sx = dgelu ? (((ai & 1) ? stgX : stgC) + c * 2048) : stgX + c * 2048;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[c][j]);
@@ -364,7 +382,6 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
             }
         }
         if (AUX && p.epilogue == 2) {
-          __syncwarp();                             // prefetched gelu' sub-tile is complete
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
             const uint4 pk = *reinterpret_cast<const uint4*>(stg64(sx, lane, ch));
@@ -394,7 +411,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
             *reinterpret_cast<uint4*>(stg64(sx, lane, ch)) = pk;
           }
         }
-        uint8_t* sc = p.out_f32 ? stgC : stgC + c * 2048;
+        uint8_t* sc = dgelu ? sx : (p.out_f32 ? stgC : stgC + c * 2048);
         if (p.out_f32) {
           if (c > 0) {                              // the single fp32 box is reused: wait until the previous store has read it
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -521,7 +538,7 @@ int num_sms() {
 template <int BN, int STAGES, int EPI_WARPS, bool AUX>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mx, TcParams p, int splits,
            cudaStream_t st) {
-  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + (AUX ? 0 : 2048) + EPI_WARPS * (4096 + (AUX ? ((BN / 32) / (EPI_WARPS / 4)) * 2048 : 0)) + 1024 + 256;
+  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + (AUX ? 0 : 2048) + EPI_WARPS * (4096 + (AUX ? ((BN / 32) / (EPI_WARPS / 4)) * 2048 : 0)) + 1024 + 512;
   static_assert(smem <= 227 * 1024, "gemm_tc: shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
@@ -586,7 +603,8 @@ int apb_gemm_tc_rowsum(const void* A, const void* B, void* C, const float* bias,
   CUtensorMap mc, mx;
   rc = make_map_out(&mc, C, p.out_f32 != 0, M, N, splits);
   if (rc) return rc;
-  rc = make_map_out(&mx, (epilogue == 1) ? aux : C, (epilogue == 1) ? false : (p.out_f32 != 0), M, N, (epilogue == 1) ? 1 : splits);
+  const bool aux_map = (epilogue == 1 || epilogue == 2);      // GELU stores gelu' through it, dGELU loads gelu' through it
+  rc = make_map_out(&mx, aux_map ? aux : C, aux_map ? false : (p.out_f32 != 0), M, N, aux_map ? 1 : splits);
   if (rc) return rc;
   const bool aux_epi = (p.epilogue == 1 || p.epilogue == 2);
   APB_CHECK_ARG(!(aux_epi && rowsum_parts != nullptr), APB_ERR_UNSUPPORTED, "gemm_tc: row sums are not available with GELU epilogues");
