@@ -148,15 +148,35 @@ __global__ void __launch_bounds__(256) bn_apply_relu_kernel(const T* __restrict_
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, T* __restrict__ y,
                                                             long long rows, int C) {
+  // the grid stride (gridDim * 256 vectors) is a multiple of C/8, so a thread always works on the same 8 channels:
+  // their scale / shift are computed once and the loop is a pure 16-byte load -> fma -> relu -> store stream
   const long long nvec = rows * (C >> 3);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % (C >> 3)) * 8;
-    float xv[8], mu[8], is[8], ga[8], be[8];
-    ld8(x + i * 8, xv);
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(i0 % (C >> 3)) * 8;
+  float a[8], b[8];
+  {
+    float mu[8], is[8], ga[8], be[8];
     ld8(mean + c0, mu); ld8(invstd + c0, is); ld8(gamma + c0, ga); ld8(beta + c0, be);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) xv[j] = fmaxf(fmaf((xv[j] - mu[j]) * is[j], ga[j], be[j]), 0.f);
-    st8(y + i * 8, xv);
+    for (int j = 0; j < 8; ++j) { a[j] = is[j] * ga[j]; b[j] = be[j] - mu[j] * a[j]; }
+  }
+  const long long step = (long long)gridDim.x * blockDim.x;
+  long long i = i0;
+  for (; i + step < nvec; i += 2 * step) {       // two vectors in flight
+    float x0[8], x1[8];
+    ld8(x + i * 8, x0);
+    ld8(x + (i + step) * 8, x1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { x0[j] = fmaxf(fmaf(x0[j], a[j], b[j]), 0.f); x1[j] = fmaxf(fmaf(x1[j], a[j], b[j]), 0.f); }
+    st8(y + i * 8, x0);
+    st8(y + (i + step) * 8, x1);
+  }
+  if (i < nvec) {
+    float x0[8];
+    ld8(x + i * 8, x0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x0[j] = fmaxf(fmaf(x0[j], a[j], b[j]), 0.f);
+    st8(y + i * 8, x0);
   }
 }
 
@@ -169,18 +189,30 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                            const float* __restrict__ dgamma,
                                                            const float* __restrict__ dbeta, T* __restrict__ dx,
                                                            long long rows, int C) {
+  // fixed 8 channels per thread (see bn_apply_relu_kernel): dx = k1 * g - k2 * x + k3 with per-channel constants
+  //   k1 = gamma*invstd, k2 = k1 * invstd * dgamma / n, k3 = k2 * mean - k1 * dbeta / n
   const long long nvec = rows * (C >> 3);
   const float inv_n = 1.f / (float)rows;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const int c0 = (int)(i % (C >> 3)) * 8;
-    float xv[8], yv[8], gv[8], mu[8], is[8], ga[8], dg[8], db[8];
-    ld8(x + i * 8, xv); ld8(y + i * 8, yv); ld8(dy + i * 8, gv);
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(i0 % (C >> 3)) * 8;
+  float k1[8], k2[8], k3[8];
+  {
+    float mu[8], is[8], ga[8], dg[8], db[8];
     ld8(mean + c0, mu); ld8(invstd + c0, is); ld8(gamma + c0, ga); ld8(dgamma + c0, dg); ld8(dbeta + c0, db);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
+      k1[j] = ga[j] * is[j];
+      k2[j] = k1[j] * is[j] * dg[j] * inv_n;
+      k3[j] = k2[j] * mu[j] - k1[j] * db[j] * inv_n;
+    }
+  }
+  for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float xv[8], yv[8], gv[8];
+    ld8(x + i * 8, xv); ld8(y + i * 8, yv); ld8(dy + i * 8, gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
       const float g = yv[j] > 0.f ? gv[j] : 0.f;
-      const float xh = (xv[j] - mu[j]) * is[j];
-      xv[j] = ga[j] * is[j] * (g - db[j] * inv_n - xh * dg[j] * inv_n);
+      xv[j] = fmaf(k1[j], g, fmaf(-k2[j], xv[j], k3[j]));
     }
     st8(dx + i * 8, xv);
   }
