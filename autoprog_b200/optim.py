@@ -108,11 +108,17 @@ class FusedAdamW(torch.optim.Optimizer):
 
     @torch.no_grad()
     def update_ema_buffers(self):
-        """ModelEmaV2 also averages buffers (BatchNorm running stats); they are tiny, so plain torch ops."""
+        """ModelEmaV2 also averages buffers (BatchNorm running stats); they are tiny, so plain torch ops -- batched
+        with the multi-tensor `_foreach_*` forms: two launches per EMA instead of two per buffer."""
         src = dict(self.flat.model.named_buffers())
         for ema, d in zip(self.ema_models, self.ema_decays):
+            fl_dst, fl_src = [], []
             for n, b in ema.named_buffers():
                 if b.dtype.is_floating_point:
-                    b.mul_(d).add_(src[n].detach(), alpha=1.0 - d)
+                    fl_dst.append(b)
+                    fl_src.append(src[n].detach())
                 else:
                     b.copy_(src[n])
+            if fl_dst:
+                torch._foreach_mul_(fl_dst, d)
+                torch._foreach_add_(fl_dst, fl_src, alpha=1.0 - d)

@@ -58,9 +58,8 @@ class DropPath(nn.Module):
         keep = 1.0 - self.drop_prob
         if self.forced:
             mask = self.forced.pop(0).to(device=device, dtype=torch.float32)
-        elif self._pooled is not None and self._pooled.shape[0] == batch:
-            rs, self._pooled = self._pooled, None
-            return rs
+        elif self._pooled and self._pooled[-1].shape[0] == batch:
+            return self._pooled.pop()
         else:
             mask = torch.floor(keep + torch.rand(batch, device=device, dtype=torch.float32))
         return (mask / keep).contiguous()
@@ -78,6 +77,8 @@ class DropPathPool:
     volo_d1).  Same distribution as the per-module draw (x / keep * floor(keep + U[0,1)), timm 0.4.5 DropPath); the
     order in which random numbers are consumed differs from the reference, which has no effect on the statistics."""
 
+    DRAWS = 2
+
     def __init__(self, model: nn.Module):
         self.mods = [m for m in model.modules() if isinstance(m, DropPath) and m.drop_prob > 0.]
         self.keep = None
@@ -87,10 +88,11 @@ class DropPathPool:
             return
         if self.keep is None or self.keep.device != device:
             self.keep = torch.tensor([1.0 - m.drop_prob for m in self.mods], device=device, dtype=torch.float32)[:, None]
-        u = torch.rand(len(self.mods), batch, device=device, dtype=torch.float32)
+        # a block calls its DropPath module once per residual branch: DRAWS independent factors per module and step
+        u = torch.rand(self.DRAWS, len(self.mods), batch, device=device, dtype=torch.float32)
         scales = u.add_(self.keep).floor_().div_(self.keep)
         for i, m in enumerate(self.mods):
-            m._pooled = scales[i]
+            m._pooled = [scales[d, i] for d in range(self.DRAWS)]
 
 
 class _ScaleRows(torch.autograd.Function):
