@@ -31,6 +31,7 @@ SIGNATURES = {
     'apb_gemm_simt': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'apb_gemm_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     'apb_gemm_tc_suggest_split': (_i, [_i, _i, _i]),
+    'apb_gemm_tc_pair': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     'apb_splitk_reduce': (_i, [_vp, _vp, _i, _ll, _vp]),
     'apb_gemm_tc_rowsum': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     'apb_gemm_tc_rowsum_slots': (_i, [_i, _i]),

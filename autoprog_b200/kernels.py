@@ -8,6 +8,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional, Sequence, Tuple
 
+import os
+
 import torch
 
 from ._lib import check, lib
@@ -156,6 +158,11 @@ def gemm(a, b, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = Fa
         check(lib().apb_gemm_simt(_p(a), _p(b), _p(out), _p(bias), _p(aux), M, N, K, int(trans_a), int(trans_b), epilogue,
                                   dt(a), _CODES[out_dtype], _st()), 'gemm_simt')
         return (out, aux) if epilogue == EPI_GELU else out
+    if (_PAIR_GEMM and not trans_a and not trans_b and epilogue == EPI_NONE and rowsum_out is None and M >= 1024
+            and out_dtype in (torch.bfloat16, torch.float32)):
+        # forward-shaped product with a tall M: CTA-pair kernel (cta_group::2), half the B-tile traffic per SM
+        check(lib().apb_gemm_tc_pair(_p(a), _p(b), _p(out), _p(bias), M, N, K, _CODES[out_dtype], _st()), 'gemm_tc_pair')
+        return out
     split = 1
     if out_dtype == torch.float32 and epilogue == EPI_NONE and bias is None:
         split = int(lib().apb_gemm_tc_suggest_split(M, N, K))
@@ -173,6 +180,9 @@ def gemm(a, b, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = Fa
     if slots > 1:
         check(lib().apb_splitk_reduce(_p(rparts), _p(rowsum_out), slots, M, _st()), 'gemm_tc(row-sum reduce)')
     return (out, aux) if epilogue == EPI_GELU else out
+
+
+_PAIR_GEMM = os.environ.get('APB_GEMM_PAIR', '0') == '1'
 
 
 def gemm_uses_tc(a: torch.Tensor, M: int, N: int, K: int) -> bool:

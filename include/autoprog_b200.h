@@ -85,6 +85,10 @@ int apb_gemm_simt(const void* A, const void* B, void* C, const float* bias, void
                   int trans_b, int epilogue, int in_dtype, int out_dtype, apb_stream_t stream);
 int apb_gemm_tc(const void* A, const void* B, void* C, const float* bias, void* aux, int M, int N, int K, int trans_a,
                 int trans_b, int epilogue, int in_dtype, int out_dtype, int split_k, apb_stream_t stream);
+/* Same product for the forward-GEMM case (A [M,K] and B [N,K] both K-major, optional bias, bf16 or fp32 out) on CTA
+ * PAIRS: tcgen05.mma.cta_group::2, 256 x 192 tile per pair, each CTA stages only half of the B tile (gemm_tc2.cu). */
+int apb_gemm_tc_pair(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, int out_dtype,
+                     apb_stream_t stream);
 /* split_k > 1 (wgrad: few output tiles, very long K): C receives split_k fp32 partial products [split_k][M][N] that
  * the caller sums in fixed order (apb_colsum over the split dim) -> deterministic; bias/epilogue must be 0/NULL. */
 int apb_gemm_tc_suggest_split(int M, int N, int K);

@@ -483,3 +483,24 @@ def test_resize_input_bilinear(shape):
     assert y.shape == (B, C, r, r) and rel(y, ref) < 3e-5, rel(y, ref)
     yb = resize_input(x.to(dev), r, torch.bfloat16)
     assert yb.dtype == torch.bfloat16 and rel(yb, ref) < 5e-3
+
+
+@pytest.mark.parametrize('M,N,Kd,f32', [(256, 192, 64, False), (1000, 384, 1152, False), (300, 136, 72, True), (25088, 384, 384, False),
+                                        (520, 1000, 384, True), (2048, 64, 152, False)])
+def test_gemm_tc_pair(M, N, Kd, f32):
+    """cta_group::2 kernel (CTA pairs, 256-row tiles): NT product with bias, ragged M / N / K tails, bf16 and fp32 out."""
+    dev = need_gpu()
+    torch.manual_seed(M + N + Kd)
+    a, b = q(torch.randn(M, Kd), torch.bfloat16), q(torch.randn(N, Kd), torch.bfloat16)
+    bias = torch.randn(N).float()
+    ref = a @ b.t() + bias.double()
+    A_, B_ = a.to(dev, torch.bfloat16), b.to(dev, torch.bfloat16)
+    out = torch.full((M, N), float('nan'), device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+    K.check(K.lib().apb_gemm_tc_pair(A_.data_ptr(), B_.data_ptr(), out.data_ptr(), bias.to(dev).data_ptr(), M, N, Kd,
+                                     K.F32 if f32 else K.BF16, st), 'gemm_tc_pair')
+    assert rel(out, ref) < (1e-5 if f32 else 5e-3), rel(out, ref)
+    out2 = torch.empty_like(out)
+    K.check(K.lib().apb_gemm_tc_pair(A_.data_ptr(), B_.data_ptr(), out2.data_ptr(), bias.to(dev).data_ptr(), M, N, Kd,
+                                     K.F32 if f32 else K.BF16, st), 'gemm_tc_pair')
+    assert torch.equal(out, out2)
