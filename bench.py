@@ -409,11 +409,25 @@ def measure_rooflines(train_step, x, t, K, torch, B, bf16):
         work = sum(w for _, _, w in rec[name])
         return ms, work, len(rec[name])
 
+    # DRAM traffic per launch from the committed ncu capture of the same step (profiles/r1_dram_traffic.json); a bench
+    # run never executes under a profiler, so these are read, not measured, here
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dram_traffic.json')))['kernels']
+    except Exception:
+        pass
+
+    def tr(name):
+        return round(traffic[name]['dram_bytes_per_launch']) if name in traffic else None
+
     gms, gflop, gn = agg('gemm')
     tf = gflop / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
     roof = {'kernel': 'gemm_tc_kernel (tcgen05) over all Linear/patchify GEMMs of one step', 'bound': 'tensor',
             'achieved': round(tf, 1), 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-            'frac': round(tf / peaks['bf16_tflops_sustained'], 4), 'traffic': None, 'launches_per_step': gn,
+            'frac': round(tf / peaks['bf16_tflops_sustained'], 4), 'traffic': tr('gemm_tc'),
+            'traffic_unit': 'DRAM bytes per launch (ncu dram__bytes_read+write, profiles/r1_dram_traffic.json); algorithmic = '
+                            + str(round(gemm_bytes / max(gn, 1))) + ' B per launch',
+            'launches_per_step': gn,
             'ms_per_step': round(gms, 3), 'peak_source': peaks['src'] + ' (sustained cuBLAS bf16)',
             # the step's GEMMs are a mix: K=192 layers of stage 1 are HBM-bound, the rest tensor-bound.  frac_binding =
             # sum over launches of max(flop time at tensor peak, algorithmic-byte time at HBM peak) / measured time
@@ -427,13 +441,18 @@ def measure_rooflines(train_step, x, t, K, torch, B, bf16):
         gbs = (fby + bby) / ((fms + bms) * 1e-3) / 1e9
         extra['roofline_outlook'] = {'kernel': 'OutlookAttention core fwd+bwd', 'bound': 'hbm', 'achieved': round(gbs, 1),
                                      'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(gbs / peaks['hbm_gbs'], 4),
-                                     'traffic': None, 'layers': fn_, 'ms_per_step': round(fms + bms, 3)}
+                                     'traffic': tr('outlook'),
+                                     'algorithmic_bytes_per_launch': round((fby + bby) / max(2 * fn_, 1)),
+                                     'layers': fn_, 'ms_per_step': round(fms + bms, 3)}
     tms, tby, _ = agg('tlce')
     if tms > 0:
         gbs = tby / (tms * 1e-3) / 1e9
         extra['roofline_tlce'] = {'kernel': 'TokenLabelCrossEntropy fused fwd+bwd', 'bound': 'hbm', 'achieved': round(gbs, 1),
                                   'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': round(gbs / peaks['hbm_gbs'], 4),
-                                  'traffic': None, 'ms_per_step': round(tms, 3)}
+                                  'traffic': (round(traffic['tlce']['dram_read_bytes'] + traffic['tlce']['dram_write_bytes'])
+                                              if 'tlce' in traffic else None),
+                                  'algorithmic_bytes_per_launch': round(tby),
+                                  'ms_per_step': round(tms, 3)}
     return roof, extra
 
 

@@ -43,7 +43,7 @@ def timed(fn):
 
 def main():
     tot_ours = tot_blas = 0.0
-    for M, N, Kd, ta, tb, epi, of32, cnt in SHAPES:
+    for M, N, Kd, ta, tb, epi, of32, cnt in SHAPES + [(25088, 1000, 384, 0, 0, 0, 0, 1), (100352, 1024, 192, 0, 0, 0, 0, 1)]:
         As = [torch.randn((Kd, M) if ta else (M, Kd), device=dev).to(bf) for _ in range(NBUF)]
         Bs = [torch.randn((Kd, N) if tb else (N, Kd), device=dev).to(bf) for _ in range(NBUF)]
         aux = torch.randn(M, N, device=dev).to(bf) if epi == 2 else None
@@ -60,12 +60,18 @@ def main():
             b = Bs[i] if tb else Bs[i].t()
             torch.matmul(a, b)          # bf16 out, no epilogue: a lower bound for what a library call costs here
 
+        t_p = None
+        if not ta and not tb and epi == 0 and not of32:
+            def pair(i):
+                K.check(K.lib().apb_gemm_tc_pair(As[i].data_ptr(), Bs[i].data_ptr(), out.data_ptr(), None, M, N, Kd, K.BF16,
+                                                 torch.cuda.current_stream().cuda_stream), 'pair')
+            t_p = timed(pair)
         t_o, t_b = timed(ours), timed(blas)
         fl = 2.0 * M * N * Kd
         tot_ours += t_o * cnt
         tot_blas += t_b * cnt
         print(f'M={M:6d} N={N:5d} K={Kd:6d} ta={ta} tb={tb} epi={epi} f32={of32} x{cnt:2d}: ours {t_o:7.1f} us {fl / t_o / 1e6:6.0f} TF/s'
-              f' | cuBLAS(plain bf16) {t_b:7.1f} us {fl / t_b / 1e6:6.0f} TF/s | split={K.lib().apb_gemm_tc_suggest_split(M, N, Kd) if of32 else 1}',
+              f' | cuBLAS(plain bf16) {t_b:7.1f} us {fl / t_b / 1e6:6.0f} TF/s | split={K.lib().apb_gemm_tc_suggest_split(M, N, Kd) if of32 else 1}' + (f' | pair(cta_group::2) {t_p:7.1f} us {fl / t_p / 1e6:6.0f} TF/s' if t_p else ''),
               flush=True)
     print(f'per-step total: ours {tot_ours / 1e3:.3f} ms, cuBLAS plain {tot_blas / 1e3:.3f} ms')
 
