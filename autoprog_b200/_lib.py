@@ -37,6 +37,7 @@ SIGNATURES = {
     'apb_gemm_tc_rowsum_slots': (_i, [_i, _i]),
     'apb_splitk_reduce2': (_i, [_vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp]),
     'apb_mhsa_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    'apb_mhsa_fwd_tc': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     'apb_mhsa_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_mhsa_fwd_simt': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_mhsa_bwd_simt': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),

@@ -113,6 +113,10 @@ int apb_splitk_reduce2(const float* parts, float* out, long long n, int splits, 
  * bwd: dqkv same layout as qkv; workspace: B*heads*N floats (row dots D_i). */
 int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, int dtype,
                  apb_stream_t stream);
+/* Opt-in variant of the forward for head_dim 32 and N <= 224: S and O accumulators in TMEM (tcgen05.mma), single-pass
+ * row softmax with one TMEM lane per query row, P fed back to the second MMA as its TMEM A operand (attention_tc.cu).
+ * Returns APB_ERR_UNSUPPORTED outside that envelope.  apb_mhsa_fwd uses it when APB_MHSA_TC=1 is set. */
+int apb_mhsa_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, apb_stream_t stream);
 /* `_simt`: CUDA-core fp32-exact kernels (parity mode, any D <= 64).  The un-suffixed entries pick the tensor-core
  * (mma.sync bf16, flash-style, scores in registers) kernels for APB_BF16 with D == 32 and the SIMT ones otherwise. */
 int apb_mhsa_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, int dtype,

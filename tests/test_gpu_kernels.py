@@ -197,7 +197,9 @@ def test_gemm_simt(M, N, Kd, ta, tb, dtype):
 
 
 @pytest.mark.parametrize('dtype', DT)
-@pytest.mark.parametrize('B,N,heads,D', [(2, 196, 2, 32), (1, 49, 3, 32), (2, 100, 1, 64), (1, 7, 2, 16), (1, 576, 1, 32)])
+@pytest.mark.parametrize('B,N,heads,D', [(2, 196, 2, 32), (1, 49, 3, 32), (2, 100, 1, 64), (1, 7, 2, 16), (1, 576, 1, 32),
+                                         (3, 197, 2, 32), (2, 144, 12, 32), (1, 224, 1, 32), (2, 64, 3, 32), (1, 1, 1, 32),
+                                         (1, 225, 2, 32), (1, 129, 1, 32)])
 def test_mhsa_core(B, N, heads, D, dtype):
     dev = need_gpu()
     torch.manual_seed(N + heads)
@@ -504,3 +506,22 @@ def test_gemm_tc_pair(M, N, Kd, f32):
     K.check(K.lib().apb_gemm_tc_pair(A_.data_ptr(), B_.data_ptr(), out2.data_ptr(), bias.to(dev).data_ptr(), M, N, Kd,
                                      K.F32 if f32 else K.BF16, st), 'gemm_tc_pair')
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize('B,N,heads', [(2, 196, 3), (1, 197, 2), (2, 64, 1), (1, 224, 2), (1, 17, 1)])
+def test_mhsa_fwd_tcgen05_variant(B, N, heads):
+    """opt-in tcgen05 / TMEM forward (attention_tc.cu: S and O accumulators in TMEM, P fed back as the TMEM A operand)
+    against the oracle, called through its own entry point."""
+    dev = need_gpu()
+    D = 32
+    torch.manual_seed(B * N + heads)
+    qkv = q(torch.randn(B, N, 3 * heads * D), torch.bfloat16)
+    ref = O.mhsa_core(qkv, heads, D ** -0.5) if hasattr(O, 'mhsa_core') else None
+    x = qkv.to(dev, torch.bfloat16)
+    out = torch.full((B, N, heads * D), float('nan'), device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, heads, N, device=dev)
+    K.check(K.lib().apb_mhsa_fwd_tc(x.data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, heads, D, D ** -0.5, torch.cuda.current_stream().cuda_stream), 'mhsa_fwd_tc')
+    out_mma, lse_mma = K.mhsa_fwd(x, heads, D ** -0.5)
+    assert rel(out, out_mma.float()) < 1e-2 and rel(lse, lse_mma) < 1e-4
+    if ref is not None:
+        assert rel(out, ref) < 2e-2
