@@ -303,10 +303,53 @@ class ClassBlock(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def forward(self, x):
-        cls = x[:, :1]
-        cls = cls + self.drop_path(self.attn(self.norm1(x))).to(cls.dtype)
+        # same arithmetic as the reference (cls = x[:, :1]; ...; cat([cls, x[:, 1:]])) with the slice / cat glue done by
+        # two small autograd Functions: the generic slice / cat backward zero-fills and re-adds [B, 1+N, C] tensors
+        # several times per block for what is a one-row update
+        cls, xt = _SplitCls.apply(x)
+        cls = cls + self.drop_path(self.attn(self.norm1(xt))).to(cls.dtype)
         cls = cls + self.drop_path(self.mlp(self.norm2(cls))).to(cls.dtype)
-        return torch.cat([cls, x[:, 1:]], dim=1)
+        return _JoinCls.apply(cls, xt, 1)
+
+
+class _SplitCls(torch.autograd.Function):
+    """x [B, 1+N, C] -> (copy of row 0, x itself).  Backward adds the cls-row gradient into row 0 of the gradient that
+    arrives for the pass-through output (a fresh tensor produced by autograd's accumulation or by _JoinCls)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.rows = x.shape[1]
+        return x[:, :1].clone(), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dcls, dx):
+        if dx is None:
+            dx = torch.zeros((dcls.shape[0], ctx.rows, dcls.shape[2]), device=dcls.device, dtype=dcls.dtype)
+        if dcls is not None:
+            dx[:, :1] += dcls
+        return dx
+
+
+class _JoinCls(torch.autograd.Function):
+    """out = [cls ; src[:, off:]] along dim 1 (off = 1: src still carries its old cls row, off = 0: src are tokens only)."""
+
+    @staticmethod
+    def forward(ctx, cls, src, off):
+        ctx.off = off
+        B, n, C = src.shape
+        out = torch.empty((B, 1 + n - off, C), device=src.device, dtype=src.dtype)
+        out[:, :1] = cls
+        out[:, 1:] = src[:, off:]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dcls = dout[:, :1].clone()
+        if ctx.off == 0:
+            return dcls, dout[:, 1:], None
+        dsrc = dout.clone()
+        dsrc[:, :1].zero_()
+        return dcls, dsrc, None
 
 
 def _make_norm(norm_layer, dim):
@@ -562,7 +605,7 @@ class VOLO(nn.Module):
 
     def forward_cls(self, x):
         cls_tokens = self.cls_token.expand(x.shape[0], -1, -1).to(x.dtype)
-        x = torch.cat((cls_tokens, x), dim=1)
+        x = _JoinCls.apply(cls_tokens, x, 0)
         for block in self.post_network:
             x = block(x)
         return x

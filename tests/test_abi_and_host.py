@@ -127,3 +127,34 @@ def test_registry_kwarg_filtering():
     assert any(getattr(mod, 'drop_prob', 0) > 0 for mod in m.modules())
     with pytest.raises(RuntimeError):
         A.create_model('nope')
+
+
+def test_class_block_glue_functions_match_slice_and_cat():
+    """ClassBlock's slice / cat glue (volo._SplitCls / _JoinCls, pure torch) == x[:, :1] ... torch.cat([cls, x[:, 1:]])
+    of the reference (models/volo.py:304-308, 634-638), values and gradients."""
+    import torch
+    from autoprog_b200.volo import _JoinCls, _SplitCls
+    torch.manual_seed(0)
+    x = torch.randn(3, 5, 4, dtype=torch.double, requires_grad=True)
+    w = torch.randn(5, 4, dtype=torch.double)
+    g = torch.randn(3, 5, 4, dtype=torch.double)
+
+    def f_ref(x):
+        cls = x[:, :1]
+        cls = cls + (x * w).sum(1, keepdim=True).tanh()
+        return torch.cat([cls * 2, x[:, 1:]], 1)
+
+    def f_new(x):
+        cls, xt = _SplitCls.apply(x)
+        cls = cls + (xt * w).sum(1, keepdim=True).tanh()
+        return _JoinCls.apply(cls * 2, xt, 1)
+
+    y1 = f_ref(x); y1.backward(g); g1 = x.grad.clone(); x.grad = None
+    y2 = f_new(x); y2.backward(g)
+    assert torch.equal(y1, y2) and torch.allclose(g1, x.grad, atol=1e-14)
+    c = torch.randn(1, 1, 4, dtype=torch.double, requires_grad=True)
+    t = torch.randn(3, 4, 4, dtype=torch.double, requires_grad=True)
+    y1 = torch.cat((c.expand(3, -1, -1), t), 1); y1.backward(g)
+    a1, b1 = c.grad.clone(), t.grad.clone(); c.grad = None; t.grad = None
+    y2 = _JoinCls.apply(c.expand(3, -1, -1), t, 0); y2.backward(g)
+    assert torch.equal(y1, y2) and torch.allclose(a1, c.grad, atol=1e-14) and torch.allclose(b1, t.grad, atol=1e-14)
