@@ -72,6 +72,20 @@ struct Geo {
   float scale;
 };
 
+// Compile-time geometry: the kernels are bound by integer / address arithmetic on the runtime geometry, so the shapes
+// of the AutoProg stages (square stage-1 grids of 16 / 20 / 24 / 28 pixels, 6 heads, untiled x axis) get instantiations in
+// which every Geo field except B and H is a constant the compiler folds.  CW = 0: fully dynamic.
+template <int CW, int CHEADS, int CTR>
+__device__ __forceinline__ Geo fix_geo(Geo g) {
+  if constexpr (CW > 0) {
+    constexpr int cw = (CW + 1) / 2;
+    g.W = CW; g.w = cw; g.heads = CHEADS; g.lpitch = (CHEADS * 81 + 7) / 8 * 8;
+    g.TR = CTR; g.nWR = CTR + 1; g.PR = 2 * CTR + 3;
+    g.TC = cw; g.nWC = cw; g.nCB = 1; g.PC = 2 * cw + 1; g.Cp = CHEADS * HD + 8;
+  }
+  return g;
+}
+
 // stage pixel rows [y0, y0+PR) x cols [x0, x0+PC) of src[b] (NHWC bf16) into s[PR][PC][Cp]; outside the image -> zeros
 template <int NT>
 __device__ __forceinline__ void stage_band(bf16* s, const bf16* __restrict__ src, const Geo& g, int b, int y0, int x0) {
@@ -221,9 +235,10 @@ __device__ __forceinline__ void gather_store(uint32_t sOut_s, bf16* __restrict__
   }
 }
 
-template <int NT>
+template <int NT, int CW, int CHEADS, int CTR>
 __global__ void __launch_bounds__(NT, 1) outlook_fwd_mma_kernel(const bf16* __restrict__ v, const bf16* __restrict__ logits,
-                                                               bf16* __restrict__ y, Geo g) {
+                                                               bf16* __restrict__ y, Geo gin) {
+  const Geo g = fix_geo<CW, CHEADS, CTR>(gin);
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* zero = reinterpret_cast<bf16*>(smraw);                                     // 64 bytes of zeros
   bf16* sV = zero + 32;
@@ -281,10 +296,11 @@ __global__ void __launch_bounds__(NT, 1) outlook_fwd_mma_kernel(const bf16* __re
   }
 }
 
-template <int NT>
+template <int NT, int CW, int CHEADS, int CTR>
 __global__ void __launch_bounds__(NT, 1) outlook_bwd_mma_kernel(const bf16* __restrict__ v, const bf16* __restrict__ logits,
                                                                const bf16* __restrict__ dy, bf16* __restrict__ dv,
-                                                               bf16* __restrict__ dlogits, Geo g) {
+                                                               bf16* __restrict__ dlogits, Geo gin) {
+  const Geo g = fix_geo<CW, CHEADS, CTR>(gin);
   extern __shared__ __align__(16) unsigned char smraw[];
   bf16* zero = reinterpret_cast<bf16*>(smraw);
   bf16* sV = zero + 32;
@@ -428,9 +444,19 @@ int apb_outlook_fwd_mma(const void* v, const void* logits, void* y, int B, int H
   size_t smem;
   if (plan(g, false, smem) != 0) return APB_ERR_UNSUPPORTED;
   constexpr int NT = 1024;
-  cudaFuncSetAttribute(outlook_fwd_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ceil_div(g.h, g.TR) * g.nCB, B);
-  outlook_fwd_mma_kernel<NT><<<grid, NT, smem, st>>>((const bf16*)v, (const bf16*)logits, (bf16*)y, g);
+#define OL_FWD(CW_, CH_, CTR_)                                                                                             \
+  do {                                                                                                                     \
+    cudaFuncSetAttribute(outlook_fwd_mma_kernel<NT, CW_, CH_, CTR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    outlook_fwd_mma_kernel<NT, CW_, CH_, CTR_><<<grid, NT, smem, st>>>((const bf16*)v, (const bf16*)logits, (bf16*)y, g);     \
+  } while (0)
+  const bool std6 = heads == 6 && lpitch == 488 && g.nCB == 1 && g.TR == 3;
+  if (std6 && W == 28) OL_FWD(28, 6, 3);
+  else if (std6 && W == 24) OL_FWD(24, 6, 3);
+  else if (std6 && W == 20) OL_FWD(20, 6, 3);
+  else if (std6 && W == 16) OL_FWD(16, 6, 3);
+  else OL_FWD(0, 0, 0);
+#undef OL_FWD
   APB_LAUNCH_CHECK("outlook_fwd_mma");
   return 0;
 }
@@ -441,10 +467,20 @@ int apb_outlook_bwd_mma(const void* v, const void* logits, const void* dy, void*
   size_t smem;
   if (plan(g, true, smem) != 0) return APB_ERR_UNSUPPORTED;
   constexpr int NT = 640;
-  cudaFuncSetAttribute(outlook_bwd_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ceil_div(g.h, g.TR) * g.nCB, B);
-  outlook_bwd_mma_kernel<NT><<<grid, NT, smem, st>>>((const bf16*)v, (const bf16*)logits, (const bf16*)dy, (bf16*)dv,
-                                                    (bf16*)dlogits, g);
+#define OL_BWD(CW_, CH_, CTR_)                                                                                             \
+  do {                                                                                                                     \
+    cudaFuncSetAttribute(outlook_bwd_mma_kernel<NT, CW_, CH_, CTR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    outlook_bwd_mma_kernel<NT, CW_, CH_, CTR_><<<grid, NT, smem, st>>>((const bf16*)v, (const bf16*)logits, (const bf16*)dy,  \
+                                                                      (bf16*)dv, (bf16*)dlogits, g);                        \
+  } while (0)
+  const bool std6 = heads == 6 && lpitch == 488 && g.nCB == 1;
+  if (std6 && W == 28 && g.TR == 2) OL_BWD(28, 6, 2);
+  else if (std6 && W == 24 && g.TR == 2) OL_BWD(24, 6, 2);
+  else if (std6 && W == 20 && g.TR == 3) OL_BWD(20, 6, 3);
+  else if (std6 && W == 16 && g.TR == 3) OL_BWD(16, 6, 3);
+  else OL_BWD(0, 0, 0);
+#undef OL_BWD
   APB_LAUNCH_CHECK("outlook_bwd_mma");
   return 0;
 }
