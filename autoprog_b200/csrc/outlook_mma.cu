@@ -466,21 +466,25 @@ int apb_outlook_bwd_mma(const void* v, const void* logits, const void* dy, void*
   Geo g = make_geo(B, H, W, heads, scale, lpitch);
   size_t smem;
   if (plan(g, true, smem) != 0) return APB_ERR_UNSUPPORTED;
-  constexpr int NT = 640;
+  // thread count: measured at 28 x 28 x 192 (one CTA / SM, so warps per CTA = latency hiding): 448 -> 275 us, 640 -> 263,
+  // 672 -> 242, 896 / 960 / 1024 -> 189 us.  The specialised geometries compile to <= 72 registers and run with 896;
+  // the dynamic-geometry kernel (90 registers) stays at 640.
   dim3 grid(ceil_div(g.h, g.TR) * g.nCB, B);
-#define OL_BWD(CW_, CH_, CTR_)                                                                                             \
-  do {                                                                                                                     \
-    cudaFuncSetAttribute(outlook_bwd_mma_kernel<NT, CW_, CH_, CTR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    outlook_bwd_mma_kernel<NT, CW_, CH_, CTR_><<<grid, NT, smem, st>>>((const bf16*)v, (const bf16*)logits, (const bf16*)dy,  \
-                                                                      (bf16*)dv, (bf16*)dlogits, g);                        \
+#define OL_BWD_NT(NT_, CW_, CH_, CTR_)                                                                                        \
+  do {                                                                                                                        \
+    cudaFuncSetAttribute(outlook_bwd_mma_kernel<NT_, CW_, CH_, CTR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    outlook_bwd_mma_kernel<NT_, CW_, CH_, CTR_><<<grid, NT_, smem, st>>>((const bf16*)v, (const bf16*)logits, (const bf16*)dy, \
+                                                                        (bf16*)dv, (bf16*)dlogits, g);                       \
   } while (0)
+#define OL_BWD(CW_, CH_, CTR_) OL_BWD_NT(896, CW_, CH_, CTR_)
   const bool std6 = heads == 6 && lpitch == 488 && g.nCB == 1;
   if (std6 && W == 28 && g.TR == 2) OL_BWD(28, 6, 2);
   else if (std6 && W == 24 && g.TR == 2) OL_BWD(24, 6, 2);
   else if (std6 && W == 20 && g.TR == 3) OL_BWD(20, 6, 3);
   else if (std6 && W == 16 && g.TR == 3) OL_BWD(16, 6, 3);
-  else OL_BWD(0, 0, 0);
+  else OL_BWD_NT(640, 0, 0, 0);
 #undef OL_BWD
+#undef OL_BWD_NT
   APB_LAUNCH_CHECK("outlook_bwd_mma");
   return 0;
 }
