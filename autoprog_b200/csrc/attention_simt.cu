@@ -206,72 +206,138 @@ __global__ void __launch_bounds__(AW * 32) mhsa_bwd_dkv_kernel(const T* __restri
   }
 }
 
-// ---- class attention: one warp per (b, head)
-template <typename T, bool BWD>
+// ---- class attention (models/volo.py:264-275): one 128-thread CTA per (b, head).  A thread owns keys t, t+128, ...
+// for everything that is "per key" (scores, dP, the dK / dV rows: whole 2*D-byte rows moved with 16-byte accesses);
+// the per-channel sums over keys (out, dq) are split over the four warps and combined through shared memory in a
+// fixed order.  The previous one-warp-per-(b, head) version walked 197 keys serially with element-wise loads.
+template <typename T>
+__device__ __forceinline__ void ca_load_row(const T* p, int D, float* dst) {
+  if constexpr (sizeof(T) == 2) {
+#pragma unroll
+    for (int c = 0; c < D; c += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p + c);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); dst[c + 2 * j] = f.x; dst[c + 2 * j + 1] = f.y; }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < D; c += 4) {
+      const float4 f = *reinterpret_cast<const float4*>(p + c);
+      dst[c] = f.x; dst[c + 1] = f.y; dst[c + 2] = f.z; dst[c + 3] = f.w;
+    }
+  }
+}
+template <typename T>
+__device__ __forceinline__ void ca_store_row(T* p, int D, const float* src, float mul) {
+  if constexpr (sizeof(T) == 2) {
+#pragma unroll
+    for (int c = 0; c < D; c += 8) {
+      uint4 u;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(src[c + 2 * j] * mul, src[c + 2 * j + 1] * mul);
+      *reinterpret_cast<uint4*>(p + c) = u;
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < D; c += 4)
+      *reinterpret_cast<float4*>(p + c) = make_float4(src[c] * mul, src[c + 1] * mul, src[c + 2] * mul, src[c + 3] * mul);
+  }
+}
+__device__ __forceinline__ float ca_block_reduce(float v, float* red, bool is_max) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();                                   // red[] may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return is_max ? fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) : ((red[0] + red[1]) + red[2]) + red[3];
+}
+
+constexpr int CA_MAXD = 64;
+// CD = compile-time head dim (32: every VOLO variant; 64) so the per-key row lives in registers; 0 = runtime D
+template <typename T, bool BWD, int CD>
 __global__ void __launch_bounds__(128) class_attn_kernel(const T* __restrict__ q, const T* __restrict__ kv,
                                                          const T* __restrict__ dout, T* __restrict__ out,
                                                          T* __restrict__ dq, T* __restrict__ dkv, int B, int N, int heads,
-                                                         int D, float scale) {
+                                                         int Drt, float scale) {
+  const int D = CD ? CD : Drt;
   extern __shared__ float sm[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* sP = sm + (size_t)warp * (2 * N + 2 * D);   // [N] p, [N] dS, [D] q*scale, [D] dO
-  float* sS = sP + N;
-  float* sQ = sS + N;
-  float* sG = sQ + D;
-  const int bh = blockIdx.x * 4 + warp;
-  if (bh >= B * heads) return;
-  const int b = bh / heads, hd = bh % heads;
+  float* sP = sm;                 // [N] probabilities
+  float* sS = sP + N;             // [N] dS (backward)
+  float* sQ = sS + N;             // [D] q * scale
+  float* sG = sQ + D;             // [D] dO (backward)
+  float* sAcc = sG + D;           // [4][D] per-warp partial channel sums
+  float* red = sAcc + 4 * D;      // [4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
   const size_t tok = (size_t)2 * heads * D;
   const T* kb = kv + (size_t)b * N * tok + (size_t)hd * D;
   const T* vb = kb + (size_t)heads * D;
   const size_t qoff = (size_t)b * heads * D + (size_t)hd * D;
-  for (int c = lane; c < D; c += 32) {
+  for (int c = tid; c < D; c += 128) {
     sQ[c] = to_f(q[qoff + c]) * scale;
     if (BWD) sG[c] = to_f(dout[qoff + c]);
   }
-  __syncwarp();
+  __syncthreads();
+  float row[CA_MAXD];
+  // ---- scores and softmax
   float m = -INFINITY;
-  for (int k = lane; k < N; k += 32) {
+  for (int k = tid; k < N; k += 128) {
+    ca_load_row(kb + (size_t)k * tok, D, row);
     float a = 0.f;
-    for (int c = 0; c < D; ++c) a = fmaf(sQ[c], to_f(kb[(size_t)k * tok + c]), a);
+#pragma unroll
+    for (int c = 0; c < D; ++c) a = fmaf(sQ[c], row[c], a);
     sP[k] = a;
     m = fmaxf(m, a);
   }
-  m = warp_max(m);
+  m = ca_block_reduce(m, red, true);
   float sum = 0.f;
-  for (int k = lane; k < N; k += 32) { const float e = expf(sP[k] - m); sP[k] = e; sum += e; }
-  sum = warp_sum(sum);
+  for (int k = tid; k < N; k += 128) { const float e = expf(sP[k] - m); sP[k] = e; sum += e; }
+  sum = ca_block_reduce(sum, red, false);
   const float inv = 1.f / sum;
-  for (int k = lane; k < N; k += 32) sP[k] *= inv;
-  __syncwarp();
-  if (!BWD) {
-    for (int c = lane; c < D; c += 32) {
-      float o = 0.f;
-      for (int k = 0; k < N; ++k) o = fmaf(sP[k], to_f(vb[(size_t)k * tok + c]), o);
-      out[qoff + c] = from_f<T>(o);
-    }
-  } else {
-    float dsum = 0.f;
-    for (int k = lane; k < N; k += 32) {
+  for (int k = tid; k < N; k += 128) sP[k] *= inv;
+  float dsum = 0.f;
+  if (BWD) {
+    for (int k = tid; k < N; k += 128) {
+      ca_load_row(vb + (size_t)k * tok, D, row);
       float dp = 0.f;
-      for (int c = 0; c < D; ++c) dp = fmaf(sG[c], to_f(vb[(size_t)k * tok + c]), dp);
+#pragma unroll
+      for (int c = 0; c < D; ++c) dp = fmaf(sG[c], row[c], dp);
       sS[k] = dp;
       dsum = fmaf(sP[k], dp, dsum);
     }
-    dsum = warp_sum(dsum);
-    for (int k = lane; k < N; k += 32) sS[k] = sP[k] * (sS[k] - dsum);
-    __syncwarp();
+    dsum = ca_block_reduce(dsum, red, false);
     T* dkb = dkv + (size_t)b * N * tok + (size_t)hd * D;
     T* dvb = dkb + (size_t)heads * D;
-    for (int c = lane; c < D; c += 32) {
-      float a = 0.f;
-      for (int k = 0; k < N; ++k) {
-        a = fmaf(sS[k], to_f(kb[(size_t)k * tok + c]), a);
-        dkb[(size_t)k * tok + c] = from_f<T>(sS[k] * sQ[c]);
-        dvb[(size_t)k * tok + c] = from_f<T>(sP[k] * sG[c]);
-      }
-      dq[qoff + c] = from_f<T>(a * scale);
+    for (int k = tid; k < N; k += 128) {
+      const float ds = sP[k] * (sS[k] - dsum);
+      sS[k] = ds;
+      ca_store_row(dkb + (size_t)k * tok, D, sQ, ds);          // dK[k] = dS[k] * (q * scale)
+      ca_store_row(dvb + (size_t)k * tok, D, sG, sP[k]);       // dV[k] = P[k] * dO
     }
+  }
+  __syncthreads();
+  // ---- per-channel sums over keys: out[c] = sum_k P[k] V[k][c]  /  dq[c] = scale * sum_k dS[k] K[k][c]
+  const float* wgt = BWD ? sS : sP;
+  const T* src = BWD ? kb : vb;
+  for (int c0 = 0; c0 < D; c0 += 32) {
+    const int c = c0 + lane;
+    float a0 = 0.f, a1 = 0.f;
+    if (c < D) {
+      int k = warp;
+      for (; k + 4 < N; k += 8) {
+        a0 = fmaf(wgt[k], to_f(src[(size_t)k * tok + c]), a0);
+        a1 = fmaf(wgt[k + 4], to_f(src[(size_t)(k + 4) * tok + c]), a1);
+      }
+      if (k < N) a0 = fmaf(wgt[k], to_f(src[(size_t)k * tok + c]), a0);
+      sAcc[warp * D + c] = a0 + a1;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < D; c += 128) {
+    const float t = ((sAcc[c] + sAcc[D + c]) + sAcc[2 * D + c]) + sAcc[3 * D + c];
+    if (BWD) dq[qoff + c] = from_f<T>(t * scale);
+    else out[qoff + c] = from_f<T>(t);
   }
 }
 
@@ -329,16 +395,20 @@ int apb_class_attn_fwd(const void* q, const void* kv, void* out, int B, int N, i
                        apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
   APB_CHECK_ARG(B > 0 && N > 0 && heads > 0 && D > 0, APB_ERR_SHAPE, "class_attn_fwd: bad shape");
-  const size_t smem = (size_t)4 * (2 * N + 2 * D) * sizeof(float);
-  APB_CHECK_ARG(smem <= 227 * 1024, APB_ERR_UNSUPPORTED, "class_attn: N=%d too large", N);
-  const int grid = ceil_div((long long)B * heads, 4);
+  const size_t smem = (size_t)(2 * N + 6 * D + 4) * sizeof(float);
+  APB_CHECK_ARG(smem <= 227 * 1024 && D <= CA_MAXD && D % 8 == 0, APB_ERR_UNSUPPORTED, "class_attn: N=%d D=%d unsupported", N, D);
+  const int grid = B * heads;
+#define CA_LAUNCH(T_, CD_, ARGS_)                                                                                  \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(class_attn_kernel<T_, false, CD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    class_attn_kernel<T_, false, CD_><<<grid, 128, smem, st>>> ARGS_;                                                 \
+  } while (0)
   if (dtype == APB_F32) {
-    cudaFuncSetAttribute(class_attn_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    class_attn_kernel<float, false><<<grid, 128, smem, st>>>((const float*)q, (const float*)kv, nullptr, (float*)out, nullptr, nullptr, B, N, heads, D, scale);
+    if (D == 32) CA_LAUNCH(float, 32, ((const float*)q, (const float*)kv, nullptr, (float*)out, nullptr, nullptr, B, N, heads, D, scale)); else if (D == 64) CA_LAUNCH(float, 64, ((const float*)q, (const float*)kv, nullptr, (float*)out, nullptr, nullptr, B, N, heads, D, scale)); else CA_LAUNCH(float, 0, ((const float*)q, (const float*)kv, nullptr, (float*)out, nullptr, nullptr, B, N, heads, D, scale));
   } else if (dtype == APB_BF16) {
-    cudaFuncSetAttribute(class_attn_kernel<bf16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    class_attn_kernel<bf16, false><<<grid, 128, smem, st>>>((const bf16*)q, (const bf16*)kv, nullptr, (bf16*)out, nullptr, nullptr, B, N, heads, D, scale);
-  } else { apb_set_error("class_attn_fwd: dtype %d", dtype); return APB_ERR_DTYPE; }
+    if (D == 32) CA_LAUNCH(bf16, 32, ((const bf16*)q, (const bf16*)kv, nullptr, (bf16*)out, nullptr, nullptr, B, N, heads, D, scale)); else if (D == 64) CA_LAUNCH(bf16, 64, ((const bf16*)q, (const bf16*)kv, nullptr, (bf16*)out, nullptr, nullptr, B, N, heads, D, scale)); else CA_LAUNCH(bf16, 0, ((const bf16*)q, (const bf16*)kv, nullptr, (bf16*)out, nullptr, nullptr, B, N, heads, D, scale));
+  } else { apb_set_error("class_attn: dtype %d", dtype); return APB_ERR_DTYPE; }
+#undef CA_LAUNCH
   APB_LAUNCH_CHECK("class_attn_fwd");
   return 0;
 }
@@ -347,16 +417,20 @@ int apb_class_attn_bwd(const void* q, const void* kv, const void* dout, void* dq
                        int D, float scale, int dtype, apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
   APB_CHECK_ARG(B > 0 && N > 0 && heads > 0 && D > 0, APB_ERR_SHAPE, "class_attn_bwd: bad shape");
-  const size_t smem = (size_t)4 * (2 * N + 2 * D) * sizeof(float);
-  APB_CHECK_ARG(smem <= 227 * 1024, APB_ERR_UNSUPPORTED, "class_attn: N=%d too large", N);
-  const int grid = ceil_div((long long)B * heads, 4);
+  const size_t smem = (size_t)(2 * N + 6 * D + 4) * sizeof(float);
+  APB_CHECK_ARG(smem <= 227 * 1024 && D <= CA_MAXD && D % 8 == 0, APB_ERR_UNSUPPORTED, "class_attn: N=%d D=%d unsupported", N, D);
+  const int grid = B * heads;
+#define CA_LAUNCH(T_, CD_, ARGS_)                                                                                  \
+  do {                                                                                                             \
+    cudaFuncSetAttribute(class_attn_kernel<T_, true, CD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    class_attn_kernel<T_, true, CD_><<<grid, 128, smem, st>>> ARGS_;                                                 \
+  } while (0)
   if (dtype == APB_F32) {
-    cudaFuncSetAttribute(class_attn_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    class_attn_kernel<float, true><<<grid, 128, smem, st>>>((const float*)q, (const float*)kv, (const float*)dout, nullptr, (float*)dq, (float*)dkv, B, N, heads, D, scale);
+    if (D == 32) CA_LAUNCH(float, 32, ((const float*)q, (const float*)kv, (const float*)dout, nullptr, (float*)dq, (float*)dkv, B, N, heads, D, scale)); else if (D == 64) CA_LAUNCH(float, 64, ((const float*)q, (const float*)kv, (const float*)dout, nullptr, (float*)dq, (float*)dkv, B, N, heads, D, scale)); else CA_LAUNCH(float, 0, ((const float*)q, (const float*)kv, (const float*)dout, nullptr, (float*)dq, (float*)dkv, B, N, heads, D, scale));
   } else if (dtype == APB_BF16) {
-    cudaFuncSetAttribute(class_attn_kernel<bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    class_attn_kernel<bf16, true><<<grid, 128, smem, st>>>((const bf16*)q, (const bf16*)kv, (const bf16*)dout, nullptr, (bf16*)dq, (bf16*)dkv, B, N, heads, D, scale);
-  } else { apb_set_error("class_attn_bwd: dtype %d", dtype); return APB_ERR_DTYPE; }
+    if (D == 32) CA_LAUNCH(bf16, 32, ((const bf16*)q, (const bf16*)kv, (const bf16*)dout, nullptr, (bf16*)dq, (bf16*)dkv, B, N, heads, D, scale)); else if (D == 64) CA_LAUNCH(bf16, 64, ((const bf16*)q, (const bf16*)kv, (const bf16*)dout, nullptr, (bf16*)dq, (bf16*)dkv, B, N, heads, D, scale)); else CA_LAUNCH(bf16, 0, ((const bf16*)q, (const bf16*)kv, (const bf16*)dout, nullptr, (bf16*)dq, (bf16*)dkv, B, N, heads, D, scale));
+  } else { apb_set_error("class_attn: dtype %d", dtype); return APB_ERR_DTYPE; }
+#undef CA_LAUNCH
   APB_LAUNCH_CHECK("class_attn_bwd");
   return 0;
 }
