@@ -35,6 +35,39 @@ __global__ void avgpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, 
   }
 }
 
+// vector form: one thread = 8 contiguous bf16 channels (16 bytes) of one output pixel
+__global__ void avgpool2_fwd_v8_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int B, int H, int W, int C, int h, int w) {
+  const int cv = C >> 3;
+  const long long n = (long long)B * h * w * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * 8;
+    long long r = idx / cv;
+    const int j = (int)(r % w); r /= w;
+    const int i = (int)(r % h);
+    const int b = (int)(r / h);
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int cnt = 0;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int yy = 2 * i + dy, xx = 2 * j + dx;
+        if (yy < H && xx < W) {
+          const uint4 u = *reinterpret_cast<const uint4*>(x + (((size_t)b * H + yy) * W + xx) * C + c);
+          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { const float2 f = __bfloat1622float2(h2[t]); s[2 * t] += f.x; s[2 * t + 1] += f.y; }
+          ++cnt;
+        }
+      }
+    uint4 o;
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) o2[t] = __floats2bfloat162_rn(s[2 * t] / (float)cnt, s[2 * t + 1] / (float)cnt);
+    *reinterpret_cast<uint4*>(y + idx * 8) = o;
+  }
+}
+
 // one thread = VEC contiguous channels (16 bytes)
 template <typename T, int VEC>
 __global__ void avgpool2_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int B, int H, int W, int C, int h, int w,
@@ -349,6 +382,11 @@ int apb_avgpool2_fwd(const void* x, void* y, int B, int H, int W, int C, int dty
   const int h = (H + 1) / 2, w = (W + 1) / 2;
   const long long n = (long long)B * h * w * C;
   if (n <= 0) return 0;
+  if (dtype == APB_BF16 && C % 8 == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0) {
+    avgpool2_fwd_v8_kernel<<<ew_grid(n / 8), EW_THREADS, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C, h, w);
+    APB_LAUNCH_CHECK("avgpool2_fwd");
+    return 0;
+  }
   DISPATCH_T(dtype, "avgpool2_fwd",
              (avgpool2_fwd_kernel<float><<<ew_grid(n), EW_THREADS, 0, st>>>((const float*)x, (float*)y, B, H, W, C, h, w)),
              (avgpool2_fwd_kernel<bf16><<<ew_grid(n), EW_THREADS, 0, st>>>((const bf16*)x, (bf16*)y, B, H, W, C, h, w)));
