@@ -9,14 +9,20 @@
 //   trans_a = 0: A is [M,K] row-major  (K-major operand)    1: A is [K,M] row-major (MN-major operand)
 //   trans_b = 0: B is [N,K] row-major  (K-major operand)    1: B is [K,N] row-major (MN-major operand)
 //
-// PERSISTENT kernel, one CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA
-// issuer, warps 2..17 = epilogue (four warps per TMEM lane quarter, each taking 32 of the tile's 128 columns: the
-// CUDA-core epilogue math needs that many warps in flight to hide its own latency).
-// Tile 128 x 128 x 64, 4-stage smem ring, TWO accumulator stages in TMEM: the epilogue of tile i overlaps the main
-// loop of tile i+1.  Epilogue warps stage their 32 x 64 sub-tile in 128B-swizzled shared memory and write it with a TMA
-// store (cp.async.bulk.tensor ... bulk_group): fully coalesced, asynchronous, and M/N tails are clipped by the TMA unit.  K is short on this path (3..18 k-blocks), so the CUDA-core epilogue (not the tensor pipe) is the
-// critical resource: GELU uses a 1.5e-7-accurate erf (Abramowitz-Stegun 7.1.26: one MUFU.RCP + one MUFU.EX2).
-// split_k > 1 writes fp32 partial tiles [split][M][N] that the caller reduces in fixed order (deterministic wgrad).
+// PERSISTENT kernel, one CTA per SM: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// 8 / 12 / 16 epilogue warps (one per TMEM lane quarter x column group).  Instantiations <BN, STAGES, EPI_WARPS, AUX>:
+//   128 x 192 tile: 4 stages, 12 epilogue warps  (3 stages when AUX: the gelu' staging boxes take the 4th stage's room)
+//   128 x 128 tile: 4 stages, 16 epilogue warps;  128 x 64 tile (stem conv, N = 64): 6 stages, 8 epilogue warps
+// TWO accumulator stages in TMEM: the epilogue of tile i overlaps the main loop of tile i+1.  Epilogue warps stage their
+// 32 x 32 sub-tiles in swizzled shared memory and write them with TMA stores (fully coalesced, asynchronous, M/N tails
+// clipped by the TMA unit).  K is short on this path (3..18 k-blocks): the main loop is bound by L2->SM operand delivery
+// (bytes in flight), the GELU epilogue by CUDA-core issue (A&S 7.1.26 erf: one MUFU.RCP + one MUFU.EX2 per element).
+//   * epilogue 1 (GELU) also stores gelu'(u) for the backward; epilogue 2 (dGELU) multiplies by it, the gelu' tiles
+//     being TMA-prefetched one tile ahead into two box sets per warp and the product written in place;
+//   * split_k > 1 writes fp32 partial tiles [split][M][N] that the caller reduces in fixed order (deterministic wgrad);
+//   * rowsum (apb_gemm_tc_rowsum): sum_k A(m,k) -- the bias gradient of a wgrad GEMM -- from one extra 128 x 16 x 16 MMA
+//     per k-step against a tile of ones, shared between the n-tiles of an m-tile.
+// The forward-shaped K >= 384 products run on CTA pairs instead (gemm_tc2.cu, cta_group::2).
 #include "gemm_tc_common.cuh"
 
 namespace {
