@@ -158,3 +158,30 @@ def test_class_block_glue_functions_match_slice_and_cat():
     a1, b1 = c.grad.clone(), t.grad.clone(); c.grad = None; t.grad = None
     y2 = _JoinCls.apply(c.expand(3, -1, -1), t, 0); y2.backward(g)
     assert torch.equal(y1, y2) and torch.allclose(a1, c.grad, atol=1e-14) and torch.allclose(b1, t.grad, atol=1e-14)
+
+
+def test_drop_path_pool_draws_once_per_step():
+    """volo.DropPathPool: one RNG call per forward provides two factors per DropPath module (one per residual branch),
+    each 0 or 1/keep as in timm 0.4.5 DropPath (x / keep * floor(keep + U)); modules fall back to their own draw after."""
+    import torch
+    import torch.nn as nn
+    from autoprog_b200.volo import DropPath, DropPathPool
+    torch.manual_seed(0)
+    net = nn.Sequential(DropPath(0.1), nn.Identity(), DropPath(0.0), DropPath(0.5)).train()
+    pool = DropPathPool(net)
+    assert len(pool.mods) == 2                              # drop_prob 0 modules are not pooled
+    pool.draw(64, torch.device('cpu'))
+    for m in pool.mods:
+        keep = 1.0 - m.drop_prob
+        a = m.sample_scale(64, torch.device('cpu'))
+        b = m.sample_scale(64, torch.device('cpu'))
+        assert not m._pooled                               # both pooled draws consumed
+        for t in (a, b):
+            assert t.shape == (64,) and bool(((t == 0) | ((t - 1.0 / keep).abs() < 1e-6)).all())
+        assert not torch.equal(a, b) or m.drop_prob == 0.0
+        c = m.sample_scale(64, torch.device('cpu'))         # third call in the same step: own draw, same law
+        assert bool(((c == 0) | ((c - 1.0 / keep).abs() < 1e-6)).all())
+    assert net[2].sample_scale(64, torch.device('cpu')) is None
+    net.eval()
+    pool.draw(64, torch.device('cpu'))
+    assert pool.mods[0].sample_scale(64, torch.device('cpu')) is None    # eval: identity
