@@ -185,3 +185,38 @@ def test_drop_path_pool_draws_once_per_step():
     net.eval()
     pool.draw(64, torch.device('cpu'))
     assert pool.mods[0].sample_scale(64, torch.device('cpu')) is None    # eval: identity
+
+
+def test_scaler_call_signature_and_update_gating():
+    """prog/scaler.py:17-74 contract: __call__(loss, optimizer, clip_grad, clip_mode, parameters, create_graph, update);
+    update=False only accumulates gradients (batch splits, main_prog.py:971), update=True clips then steps."""
+    import torch
+    import torch.nn as nn
+    from autoprog_b200.scaler import ApexScaler, Bf16Scaler, NoScaler, dispatch_clip_grad
+    assert ApexScaler is Bf16Scaler and issubclass(Bf16Scaler, NoScaler) and Bf16Scaler.state_dict_key == 'bf16_scaler'
+    torch.manual_seed(0)
+    lin = nn.Linear(4, 3)
+    opt = torch.optim.SGD(lin.parameters(), lr=0.1)
+    x, y = torch.randn(5, 4), torch.randn(5, 3)
+    w0 = lin.weight.detach().clone()
+    sc = Bf16Scaler()
+    sc(((lin(x) - y) ** 2).mean(), opt, update=False)
+    g1 = lin.weight.grad.clone()
+    assert torch.equal(lin.weight, w0)                                  # no step yet
+    sc(((lin(x) - y) ** 2).mean(), opt, clip_grad=1e-3, clip_mode='norm', parameters=lin.parameters(), update=True)
+    assert not torch.equal(lin.weight, w0)
+    total = torch.sqrt(sum((p.grad ** 2).sum() for p in lin.parameters()))
+    assert float(total) <= 1e-3 * 1.001                                 # accumulated (2 x g1) gradient was clipped
+    assert torch.allclose(lin.weight.grad / lin.weight.grad.norm(), g1 / g1.norm(), atol=1e-6)
+    assert sc.state_dict() is None
+    for mode in ('value', 'agc'):
+        lin.zero_grad()
+        ((lin(x) - y) ** 2).mean().backward()
+        dispatch_clip_grad(list(lin.parameters()), 1e-4, mode=mode)
+        if mode == 'value':
+            assert float(lin.weight.grad.abs().max()) <= 1e-4 + 1e-12
+    try:
+        dispatch_clip_grad(list(lin.parameters()), 1.0, mode='nope')
+        raise RuntimeError('expected AssertionError')
+    except AssertionError:
+        pass
