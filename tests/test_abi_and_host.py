@@ -220,3 +220,54 @@ def test_scaler_call_signature_and_update_gating():
         raise RuntimeError('expected AssertionError')
     except AssertionError:
         pass
+
+
+def test_flat_state_grouping_alignment_and_views():
+    """flat.FlatState: timm's no-weight-decay rule (ndim <= 1, '.bias', model.no_weight_decay()), 8-element aligned
+    slices in reverse registration order, parameters / gradients re-pointed into the flat buffers, EMA copies laid
+    out identically, and ensure_grad_views() adopting gradients autograd allocated itself."""
+    import copy
+    import torch
+    import torch.nn as nn
+    from autoprog_b200.flat import FlatState, split_decay
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.pos_embed = nn.Parameter(torch.randn(1, 3, 5))
+            self.fc = nn.Linear(5, 7)
+            self.norm = nn.LayerNorm(7)
+
+        def no_weight_decay(self):
+            return {'pos_embed'}
+
+        def forward(self, x):
+            return self.norm(self.fc(x + self.pos_embed))
+
+    torch.manual_seed(0)
+    net = Net()
+    decay, no_decay = split_decay(net, 0.05)
+    assert [n for n, _ in decay] == ['fc.weight']
+    assert sorted(n for n, _ in no_decay) == ['fc.bias', 'norm.bias', 'norm.weight', 'pos_embed']
+    ref = {n: p.detach().clone() for n, p in net.named_parameters()}
+    ema = copy.deepcopy(net)
+    flat = FlatState(net, weight_decay=0.05, want_shadow=False)
+    assert flat.weight_decays == [0.05, 0.0]
+    for g in flat.groups:
+        assert all(o % 8 == 0 for o in g.offsets) and g.numel % 8 == 0
+        for p, o in zip(g.params, g.offsets):
+            assert p.data_ptr() == g.flat_p[o:].data_ptr()                   # parameter lives in the flat buffer
+    assert flat.groups[1].names == ['norm.bias', 'norm.weight', 'fc.bias', 'pos_embed']   # reverse registration order
+    for n, p in net.named_parameters():
+        assert torch.equal(p, ref[n])
+    ema_flats = flat.flat_like(ema)
+    for g, ef in zip(flat.groups, ema_flats):
+        assert ef.shape == g.flat_p.shape and torch.equal(ef, g.flat_p)      # same layout, same (copied) values
+    flat.zero_grad()
+    assert all(p.grad is None for p in net.parameters())
+    net(torch.randn(2, 3, 5)).sum().backward()                               # CPU: autograd allocates the gradients
+    auto = {n: p.grad.clone() for n, p in net.named_parameters()}
+    flat.ensure_grad_views()
+    for g in flat.groups:
+        for n, p, o in zip(g.names, g.params, g.offsets):
+            assert p.grad.data_ptr() == g.flat_g[o:].data_ptr() and torch.equal(p.grad, auto[n])
