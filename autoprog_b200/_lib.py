@@ -65,6 +65,8 @@ SIGNATURES = {
     'apb_bn_relu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     'apb_adamw_ema': (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, C.POINTER(_vp), C.POINTER(_f), _i, _vp, _vp]),
     'apb_launch_count': (_ll, []),
+    'apb_fallback_count': (_ll, []),
+    'apb_debug_umma_probe': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
 }
 
 _lib = None

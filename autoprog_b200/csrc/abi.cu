@@ -16,3 +16,11 @@ extern "C" int apb_abi_version(void) { return 1; }
 
 long long g_apb_launches = 0;
 extern "C" long long apb_launch_count(void) { return g_apb_launches; }
+
+// bf16 calls that fell through to a CUDA-core kernel because the tensor-core kernel declined the shape
+long long g_apb_fallbacks = 0;
+extern "C" long long apb_fallback_count(void) { return g_apb_fallbacks; }
+void apb_note_fallback(const char* what, const char* why) {
+  ++g_apb_fallbacks;
+  if (g_apb_fallbacks <= 8) fprintf(stderr, "[autoprog_b200] %s: tensor-core kernel declined (%s); running the CUDA-core kernel\n", what, why);
+}

@@ -23,6 +23,7 @@ void apb_set_error(const char* fmt, ...);
     }                                             \
   } while (0)
 
+void apb_note_fallback(const char* what, const char* why);   // counted + logged: a bf16 call served by a CUDA-core kernel
 extern long long g_apb_launches;   // kernel launches issued through the library (not thread-exact; evidence counter)
 #define APB_LAUNCH_CHECK(name)                                              \
   do {                                                                      \

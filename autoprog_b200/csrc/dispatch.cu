@@ -14,6 +14,7 @@ int apb_outlook_fwd(const void* v, const void* logits, void* y, int B, int H, in
     const int rc = apb_outlook_fwd_mma(v, logits, y, B, H, W, heads, scale, lpitch, APB_STREAM(stream));
     if (rc != APB_ERR_UNSUPPORTED) return rc;
   }
+  if (dtype == APB_BF16) apb_note_fallback("outlook_fwd", "shape / alignment outside the tensor-core kernel's envelope");
   return apb_outlook_fwd_simt(v, logits, y, B, H, W, heads, scale, lpitch, dtype, stream);
 }
 
@@ -24,6 +25,7 @@ int apb_outlook_bwd(const void* v, const void* logits, const void* dy, void* dv,
     const int rc = apb_outlook_bwd_mma(v, logits, dy, dv, dlogits, B, H, W, heads, scale, lpitch, APB_STREAM(stream));
     if (rc != APB_ERR_UNSUPPORTED) return rc;
   }
+  if (dtype == APB_BF16) apb_note_fallback("outlook_bwd", "shape / alignment outside the tensor-core kernel's envelope");
   return apb_outlook_bwd_simt(v, logits, dy, dv, dlogits, B, H, W, heads, scale, lpitch, dtype, stream);
 }
 
@@ -47,6 +49,7 @@ int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads
     const int rc = apb_mhsa_fwd_mma(qkv, out, lse, B, N, heads, D, scale, APB_STREAM(stream));
     if (rc != APB_ERR_UNSUPPORTED) return rc;
   }
+  if (dtype == APB_BF16) apb_note_fallback("mhsa_fwd", "head_dim not 32 / 64 or N too large for shared memory");
   return apb_mhsa_fwd_simt(qkv, out, lse, B, N, heads, D, scale, dtype, stream);
 }
 
@@ -56,5 +59,6 @@ int apb_mhsa_bwd(const void* qkv, const void* out, const void* dout, const float
     const int rc = apb_mhsa_bwd_mma(qkv, out, dout, lse, dqkv, workspace, B, N, heads, D, scale, APB_STREAM(stream));
     if (rc != APB_ERR_UNSUPPORTED) return rc;
   }
+  if (dtype == APB_BF16) apb_note_fallback("mhsa_bwd", "head_dim not 32 / 64 or N too large for shared memory");
   return apb_mhsa_bwd_simt(qkv, out, dout, lse, dqkv, workspace, B, N, heads, D, scale, dtype, stream);
 }

@@ -108,6 +108,13 @@ class FlatState:
         for g in self.groups:
             g.zero_grad()
 
+    @torch.no_grad()
+    def refresh_shadows(self):
+        """Re-cast the bf16 compute copies from the fp32 parameters (after a load that wrote the parameters in place)."""
+        for g in self.groups:
+            if g.shadow is not None:
+                g.shadow.copy_(g.flat_p)
+
     def ensure_grad_views(self):
         for g in self.groups:
             g.ensure_grad_views()

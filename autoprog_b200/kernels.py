@@ -418,3 +418,8 @@ def adamw_ema(p, g, m, v, hyper, beta1, beta2, eps, wd, emas=(), decays=(), shad
 
 def launch_count() -> int:
     return int(lib().apb_launch_count())
+
+
+def fallback_count() -> int:
+    """bf16 calls that a tensor-core kernel declined and a CUDA-core kernel served (each one is also logged on stderr)."""
+    return int(lib().apb_fallback_count())

@@ -48,8 +48,16 @@ def wcast(p: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
         return src
     key = id(p)
     ent = _WCACHE.get(key)
-    if ent is not None and ent[1] == p.data_ptr() and ent[2].shape == p.shape and (ent[3] or ent[0] == p._version):
-        return ent[2]
+    if ent is not None and ent[1] == p.data_ptr() and ent[2].shape == p.shape and ent[2].dtype == dtype:
+        if ent[0] == p._version:
+            return ent[2]
+        if ent[3]:
+            # optimizer-owned shadow (the fused step keeps it fresh without bumping `_version`), but the parameter was
+            # written in place since (load_state_dict, MoGrow loaders, resume): re-cast INTO the owner's buffer
+            K.check(K.lib().apb_cast(src.data_ptr(), ent[2].data_ptr(), src.numel(), K.dt(src), K._CODES[dtype],
+                                     torch.cuda.current_stream().cuda_stream), 'cast(shadow refresh)')
+            _WCACHE[key] = (p._version, ent[1], ent[2], True)
+            return ent[2]
     t = K.cast(src, dtype)
     if ent is None:
         weakref.finalize(p, _WCACHE.pop, key, None)
@@ -61,7 +69,7 @@ def register_shadow(p: torch.Tensor, shadow: torch.Tensor) -> None:
     """Let a fused optimizer publish the bf16 copy it wrote (skips the cast kernel on the next forward)."""
     if id(p) not in _WCACHE:
         weakref.finalize(p, _WCACHE.pop, id(p), None)
-    _WCACHE[id(p)] = (p._version, p.data_ptr(), shadow, True)   # True: kept fresh by its owner, never stale
+    _WCACHE[id(p)] = (p._version, p.data_ptr(), shadow, True)   # True: owner-refreshed; stale only after an in-place write
 
 
 def invalidate_derived_caches() -> None:

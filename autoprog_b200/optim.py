@@ -98,6 +98,49 @@ class FusedAdamW(torch.optim.Optimizer):
                         group['weight_decay'], [ef[gi] for ef in self.ema_flats], self.ema_decays, g.shadow)
         ops.invalidate_derived_caches()
 
+    # ---- checkpointing: torch.optim.AdamW layout (per-parameter `step` / `exp_avg` / `exp_avg_sq`), so what the
+    # reference's CheckpointSaver stores (`optimizer.state_dict()`, main_prog.py:600-606) and `resume_checkpoint`
+    # reloads interchanges with a stock AdamW built over the same parameter order
+    def state_dict(self):
+        state, groups, idx = {}, [], 0
+        for gi, (g, group) in enumerate(zip(self.flat.groups, self.param_groups)):
+            ids = []
+            for m, v in zip(g.views(self.exp_avg[gi]), g.views(self.exp_avg_sq[gi])):
+                state[idx] = {'step': torch.tensor(float(self.step_count)), 'exp_avg': m.detach().clone(),
+                              'exp_avg_sq': v.detach().clone()}
+                ids.append(idx)
+                idx += 1
+            pg = {k: v for k, v in group.items() if k != 'params'}
+            for k, v in (('amsgrad', False), ('maximize', False), ('foreach', None), ('capturable', False),
+                         ('differentiable', False), ('fused', None), ('decoupled_weight_decay', True)):
+                pg.setdefault(k, v)           # the keys torch.optim.AdamW's step() looks up in a loaded group
+            pg['params'] = ids
+            groups.append(pg)
+        return {'state': state, 'param_groups': groups}
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        groups = state_dict['param_groups']
+        if len(groups) != len(self.param_groups) or any(len(a['params']) != len(b['params'])
+                                                         for a, b in zip(groups, self.param_groups)):
+            raise ValueError('FusedAdamW.load_state_dict: parameter groups do not match this optimizer')
+        st = state_dict['state']
+        steps = set()
+        for gi, (g, saved, group) in enumerate(zip(self.flat.groups, groups, self.param_groups)):
+            group.update({k: v for k, v in saved.items() if k != 'params'})
+            for pid, m, v in zip(saved['params'], g.views(self.exp_avg[gi]), g.views(self.exp_avg_sq[gi])):
+                ent = st.get(pid, st.get(str(pid)))
+                if ent is None:            # parameter that never received a gradient in the saved run
+                    m.zero_(); v.zero_()
+                    continue
+                m.copy_(ent['exp_avg'].reshape(m.shape))
+                v.copy_(ent['exp_avg_sq'].reshape(v.shape))
+                steps.add(int(float(ent['step'])))
+        if len(steps) > 1:
+            raise ValueError(f'FusedAdamW.load_state_dict: one step counter for all parameters is required, got {sorted(steps)}')
+        self.step_count = steps.pop() if steps else 0
+        self.flat.refresh_shadows()        # a resume usually loads the model weights next to the optimizer state
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None

@@ -8,6 +8,13 @@ fp16 GradScaler flow for callers that insist on it.  Apex is not required.
 import torch
 
 
+def unitwise_norm(x, norm_type=2.0):
+    """timm.utils.agc.unitwise_norm: whole-tensor norm for scalars / vectors, per-unit (dim 0) norm otherwise."""
+    if x.ndim <= 1:
+        return x.norm(norm_type)
+    return x.norm(norm_type, dim=tuple(range(1, x.ndim)), keepdim=True)
+
+
 def dispatch_clip_grad(parameters, value, mode='norm', norm_type=2.0):
     """timm.utils.clip_grad.dispatch_clip_grad ('norm' | 'value' | 'agc')."""
     if mode == 'norm':
@@ -15,13 +22,15 @@ def dispatch_clip_grad(parameters, value, mode='norm', norm_type=2.0):
     elif mode == 'value':
         torch.nn.utils.clip_grad_value_(parameters, value)
     elif mode == 'agc':
+        # timm adaptive_clip_grad: UNIT-wise norms (per output row for ndim > 1 tensors), eps 1e-3 on the parameter norm
         for p in parameters:
             if p.grad is None:
                 continue
-            pn = p.detach().norm(norm_type).clamp_(min=1e-3)
-            gn = p.grad.detach().norm(norm_type)
-            clipped = p.grad * (pn * value / gn.clamp(min=1e-6))
-            p.grad.detach().copy_(torch.where(gn < pn * value, p.grad, clipped))
+            pd, g = p.detach(), p.grad.detach()
+            max_norm = unitwise_norm(pd, norm_type).clamp_(min=1e-3).mul_(value)
+            gn = unitwise_norm(g, norm_type)
+            clipped = g * (max_norm / gn.clamp(min=1e-6))
+            g.copy_(torch.where(gn < max_norm, g, clipped))
     else:
         raise AssertionError(f'Unknown clip mode ({mode}).')
 

@@ -200,6 +200,14 @@ int apb_adamw_ema(float* p, const float* g, float* m, float* v, long long n, con
 
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches evidence) */
 long long apb_launch_count(void);
+/* number of bf16 calls whose tensor-core kernel declined the shape (APB_ERR_UNSUPPORTED) and that were served by a
+ * CUDA-core kernel instead; each one also prints a line on stderr.  bench.py asserts / reports it (must stay 0 on the
+ * benchmark configurations). */
+long long apb_fallback_count(void);
+
+/* diagnostic (tools/umma_probe.py): D[128,32] = A[128,64] * B[64, off:off+32] through ONE descriptor convention
+ * (mode 0..3, see csrc/umma_probe.cu); pins the shared-memory layouts the attention kernels rely on. */
+int apb_debug_umma_probe(const void* A, const void* Bm, float* D, int mode, int off_elems, apb_stream_t stream);
 
 #ifdef __cplusplus
 }

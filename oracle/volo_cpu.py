@@ -296,8 +296,8 @@ def bilinear_matrix(n_in: int, n_out: int) -> Tensor:
 
 def resize_input(x: Tensor, r: int) -> Tensor:
     """x [B,C,H,W] -> [B,C,r,r], the trainer's per-step bilinear resolution switch (main_prog.py:973-974)."""
-    My = bilinear_matrix(x.shape[2], r).to(x.dtype)
-    Mx = bilinear_matrix(x.shape[3], r).to(x.dtype)
+    My = bilinear_matrix(x.shape[2], r).to(x)
+    Mx = bilinear_matrix(x.shape[3], r).to(x)
     return torch.einsum('yh,xw,bchw->bcyx', My, Mx, x)
 
 
@@ -306,8 +306,8 @@ def pos_embed_resize(pos: Tensor, h0: int, w0: int) -> Tensor:
     _, h, w, C = pos.shape
     if h == h0 and w == w0:
         return pos
-    My = bicubic_matrix(h, h0).to(pos.dtype)
-    Mx = bicubic_matrix(w, w0).to(pos.dtype)
+    My = bicubic_matrix(h, h0).to(pos)
+    Mx = bicubic_matrix(w, w0).to(pos)
     return torch.einsum('yh,xw,bhwc->byxc', My, Mx, pos)
 
 

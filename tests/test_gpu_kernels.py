@@ -525,3 +525,26 @@ def test_mhsa_fwd_tcgen05_variant(B, N, heads):
     assert rel(out, out_mma.float()) < 1e-2 and rel(lse, lse_mma) < 1e-4
     if ref is not None:
         assert rel(out, ref) < 2e-2
+
+
+@pytest.mark.parametrize('dtype', DT)
+def test_tlce_gt_variant_gradients(dtype):
+    """TokenLabelGTCrossEntropy (loss/cross_entropy.py:62-89): loss AND gradients against autograd through the oracle's
+    restatement (gt_mix=True), including a case where ground truth and cls target agree (ratio 0.5) and a mixed box."""
+    dev = need_gpu()
+    import autoprog_b200 as A
+    torch.manual_seed(17)
+    B, N, C = 6, 16, 40
+    xc, xa = q(torch.randn(B, C) * 2, dtype), q(torch.randn(B, N, C) * 2, dtype)
+    t = torch.softmax(torch.randn(B, C, 2 + N) * 2, 1).float()
+    t[:3, :, 0] = t[:3, :, 1]                     # argmax agrees for the first three samples -> ratio 0.5
+    for bbox in [(0, 0, 0, 0), (1, 0, 3, 2)]:
+        xcr, xar = xc.double().requires_grad_(True), xa.double().requires_grad_(True)
+        ref = O.token_label_ce(xcr, xar, bbox, t.double(), dense_weight=0.5, cls_weight=1.0, gt_mix=True)
+        ref.backward()
+        xcd, xad = xc.to(dev, dtype).requires_grad_(True), xa.to(dev, dtype).requires_grad_(True)
+        loss = A.TokenLabelGTCrossEntropy(dense_weight=0.5, cls_weight=1.0, classes=C)((xcd, xad, bbox), t.to(dev))
+        loss.backward()
+        tl = tol(dtype)
+        assert abs(float(loss) - float(ref)) < 2e-6 * abs(float(ref)) + 1e-7
+        assert rel(xcd.grad, xcr.grad) < tl and rel(xad.grad, xar.grad) < tl, (rel(xcd.grad, xcr.grad), rel(xad.grad, xar.grad))
