@@ -38,6 +38,9 @@ SIGNATURES = {
     'apb_splitk_reduce2': (_i, [_vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp]),
     'apb_mhsa_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_mhsa_fwd_tc': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    'apb_mhsa_bwd_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    'apb_mhsa_fwd_mma': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    'apb_mhsa_bwd_mma': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     'apb_mhsa_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_mhsa_fwd_simt': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_mhsa_bwd_simt': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),

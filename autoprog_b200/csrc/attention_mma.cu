@@ -455,14 +455,16 @@ static int mhsa_bwd_mma_t(const void* qkv, const void* out, const void* dout, co
 }
 
 // D = 32 or 64; anything else -> APB_ERR_UNSUPPORTED (the dispatcher then uses the SIMT kernels)
-int apb_mhsa_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, cudaStream_t st) {
+int apb_mhsa_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, apb_stream_t stream) {
+  cudaStream_t st = APB_STREAM(stream);
   if (D == 32) return mhsa_fwd_mma_t<32>(qkv, out, lse, B, N, heads, scale, st);
   if (D == 64) return mhsa_fwd_mma_t<64>(qkv, out, lse, B, N, heads, scale, st);
   return APB_ERR_UNSUPPORTED;
 }
 
 int apb_mhsa_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
-                     int B, int N, int heads, int D, float scale, cudaStream_t st) {
+                     int B, int N, int heads, int D, float scale, apb_stream_t stream) {
+  cudaStream_t st = APB_STREAM(stream);
   if (D == 32) return mhsa_bwd_mma_t<32>(qkv, out, dout, lse, dqkv, workspace, B, N, heads, scale, st);
   if (D == 64) return mhsa_bwd_mma_t<64>(qkv, out, dout, lse, dqkv, workspace, B, N, heads, scale, st);
   return APB_ERR_UNSUPPORTED;

@@ -29,24 +29,18 @@ int apb_outlook_bwd(const void* v, const void* logits, const void* dy, void* dv,
   return apb_outlook_bwd_simt(v, logits, dy, dv, dlogits, B, H, W, heads, scale, lpitch, dtype, stream);
 }
 
-int apb_mhsa_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, cudaStream_t st);
-int apb_mhsa_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
-                     int B, int N, int heads, int D, float scale, cudaStream_t st);
-
-// bf16 + head_dim 32, N <= 224 (every VOLO stage-2 grid up to 224 px) -> tcgen05 / TMEM forward (attention_tc.cu);
-// bf16 + head_dim 32 / 64 otherwise -> mma.sync kernels (attention_mma.cu); anything else -> CUDA-core fp32 kernels
+// bf16, head_dim 32, N <= 224 (every VOLO stage-2 grid up to 224 px) -> tcgen05 / TMEM / TMA kernels (attention_tc.cu),
+// forward and backward; bf16 with head_dim 64 (DeiT) or longer sequences (volo_d2 @ 384: N = 576) -> flash-style mma.sync
+// kernels (attention_mma.cu); fp32 -> CUDA-core parity kernels.  A bf16 call that ends on the CUDA cores is counted and
+// logged (apb_fallback_count).
 int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, int dtype,
                  apb_stream_t stream) {
-  // opt-in (APB_MHSA_TC=1): numerically validated (tests/test_gpu_kernels.py::test_mhsa_core) but, with one 128-thread
-  // CTA per (b, head) and TMEM limiting an SM to two of them, it is latency-bound: 124 us vs 72 us for the mma.sync
-  // kernel at B=128, N=196, 12 heads (see the file header of attention_tc.cu for what a faster version needs)
-  static const bool use_tc = getenv("APB_MHSA_TC") && atoi(getenv("APB_MHSA_TC")) == 1;
-  if (use_tc && dtype == APB_BF16 && D == 32 && B > 0 && N > 0 && N <= 224 && heads > 0) {
+  if (dtype == APB_BF16 && D == 32 && B > 0 && N > 0 && N <= 224 && heads > 0) {
     const int rc = apb_mhsa_fwd_tc(qkv, out, lse, B, N, heads, D, scale, stream);
     if (rc != APB_ERR_UNSUPPORTED) return rc;
   }
   if (dtype == APB_BF16 && (D == 32 || D == 64) && B > 0 && N > 0 && heads > 0) {
-    const int rc = apb_mhsa_fwd_mma(qkv, out, lse, B, N, heads, D, scale, APB_STREAM(stream));
+    const int rc = apb_mhsa_fwd_mma(qkv, out, lse, B, N, heads, D, scale, stream);
     if (rc != APB_ERR_UNSUPPORTED) return rc;
   }
   if (dtype == APB_BF16) apb_note_fallback("mhsa_fwd", "head_dim not 32 / 64 or N too large for shared memory");
@@ -55,8 +49,12 @@ int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads
 
 int apb_mhsa_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
                  int B, int N, int heads, int D, float scale, int dtype, apb_stream_t stream) {
+  if (dtype == APB_BF16 && D == 32 && B > 0 && N > 0 && N <= 224 && heads > 0) {
+    const int rc = apb_mhsa_bwd_tc(qkv, out, dout, lse, dqkv, B, N, heads, D, scale, stream);
+    if (rc != APB_ERR_UNSUPPORTED) return rc;
+  }
   if (dtype == APB_BF16 && (D == 32 || D == 64) && B > 0 && N > 0 && heads > 0) {
-    const int rc = apb_mhsa_bwd_mma(qkv, out, dout, lse, dqkv, workspace, B, N, heads, D, scale, APB_STREAM(stream));
+    const int rc = apb_mhsa_bwd_mma(qkv, out, dout, lse, dqkv, workspace, B, N, heads, D, scale, stream);
     if (rc != APB_ERR_UNSUPPORTED) return rc;
   }
   if (dtype == APB_BF16) apb_note_fallback("mhsa_bwd", "head_dim not 32 / 64 or N too large for shared memory");

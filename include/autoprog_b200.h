@@ -113,12 +113,21 @@ int apb_splitk_reduce2(const float* parts, float* out, long long n, int splits, 
  * bwd: dqkv same layout as qkv; workspace: B*heads*N floats (row dots D_i). */
 int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, int dtype,
                  apb_stream_t stream);
-/* Opt-in variant of the forward for head_dim 32 and N <= 224: S and O accumulators in TMEM (tcgen05.mma), single-pass
- * row softmax with one TMEM lane per query row, P fed back to the second MMA as its TMEM A operand (attention_tc.cu).
- * Returns APB_ERR_UNSUPPORTED outside that envelope.  apb_mhsa_fwd uses it when APB_MHSA_TC=1 is set. */
+/* tcgen05 / TMEM / TMA kernels for head_dim 32 and N <= 224 (attention_tc.cu): S (and dP) accumulate in TMEM, one TMEM
+ * lane per query row (plain two-pass row softmax, no shuffles), P fed back as the TMEM A operand (forward) or through
+ * 64B-swizzled shared tiles read K-major and MN-major (backward: dV, dK, dQ in ONE kernel, row dots computed in-kernel).
+ * Return APB_ERR_UNSUPPORTED outside that envelope.  apb_mhsa_fwd / apb_mhsa_bwd use them by default for APB_BF16. */
 int apb_mhsa_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, apb_stream_t stream);
-/* `_simt`: CUDA-core fp32-exact kernels (parity mode, any D <= 64).  The un-suffixed entries pick the tensor-core
- * (mma.sync bf16, flash-style, scores in registers) kernels for APB_BF16 with D == 32 and the SIMT ones otherwise. */
+int apb_mhsa_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int N, int heads,
+                    int D, float scale, apb_stream_t stream);
+/* flash-style mma.sync kernels (attention_mma.cu; bf16, head_dim 32 or 64, any N that fits shared memory): scores in
+ * registers, online softmax; bwd = row-dot + dQ + dK/dV kernels.  workspace: B*heads*N floats. */
+int apb_mhsa_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, apb_stream_t stream);
+int apb_mhsa_bwd_mma(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
+                     int B, int N, int heads, int D, float scale, apb_stream_t stream);
+/* `_simt`: CUDA-core fp32-exact kernels (parity mode, any D <= 64).  The un-suffixed entries pick, for APB_BF16, the
+ * tcgen05 kernels above (D == 32, N <= 224) or the flash-style mma.sync kernels (D == 64, or longer sequences), and the
+ * SIMT ones for APB_F32. */
 int apb_mhsa_fwd_simt(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, int dtype,
                       apb_stream_t stream);
 int apb_mhsa_bwd_simt(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,

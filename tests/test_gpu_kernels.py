@@ -539,10 +539,10 @@ def test_tlce_gt_variant_gradients(dtype):
     t = torch.softmax(torch.randn(B, C, 2 + N) * 2, 1).float()
     t[:3, :, 0] = t[:3, :, 1]                     # argmax agrees for the first three samples -> ratio 0.5
     for bbox in [(0, 0, 0, 0), (1, 0, 3, 2)]:
-        xcr, xar = xc.double().requires_grad_(True), xa.double().requires_grad_(True)
+        xcr, xar = xc.clone().requires_grad_(True), xa.clone().requires_grad_(True)
         ref = O.token_label_ce(xcr, xar, bbox, t.double(), dense_weight=0.5, cls_weight=1.0, gt_mix=True)
         ref.backward()
-        xcd, xad = xc.to(dev, dtype).requires_grad_(True), xa.to(dev, dtype).requires_grad_(True)
+        xcd, xad = xc.detach().to(dev, dtype).requires_grad_(True), xa.detach().to(dev, dtype).requires_grad_(True)
         loss = A.TokenLabelGTCrossEntropy(dense_weight=0.5, cls_weight=1.0, classes=C)((xcd, xad, bbox), t.to(dev))
         loss.backward()
         tl = tol(dtype)
