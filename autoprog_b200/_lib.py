@@ -38,7 +38,7 @@ SIGNATURES = {
     'apb_splitk_reduce2': (_i, [_vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp]),
     'apb_mhsa_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_mhsa_fwd_tc': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
-    'apb_mhsa_bwd_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+    'apb_mhsa_bwd_tc': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     'apb_mhsa_fwd_mma': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     'apb_mhsa_bwd_mma': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     'apb_mhsa_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
@@ -70,6 +70,8 @@ SIGNATURES = {
     'apb_launch_count': (_ll, []),
     'apb_fallback_count': (_ll, []),
     'apb_debug_umma_probe': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    'apb_debug_umma_timing': (_i, [_vp, _i, _i, _i, _vp]),
+    'apb_debug_mhsa_trace': (_i, [_vp]),
 }
 
 _lib = None

@@ -99,6 +99,10 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// lane 0's view of the barrier, broadcast: keeps polling loops warp-uniform
+__device__ __forceinline__ bool mbar_test_u(uint64_t* bar, uint32_t parity) {
+  return __shfl_sync(0xffffffffu, mbar_test(bar, parity) ? 1u : 0u, 0) != 0;
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -124,11 +128,26 @@ struct AttParams {
   const bf16* dout;    // bwd
   bf16* out;           // fwd: [B, N, heads*32]; bwd: dqkv
   float* lse;          // [B, heads, N]
+  const float* rowdot; // bwd: [B, heads, N] D = sum_d dO * O (written by mhsa_rowdot_tc_kernel)
   int B, N, heads;
   int Npad;            // keys padded to a multiple of 16
   int ntq;             // query tiles of 128 rows
   int units;           // B * heads
   float scale;
+  long long* trace;    // optional (diagnostic): [18 warps][TRACE_MAX] {event id << 48 | clock} written by CTA 0
+};
+
+constexpr int TRACE_MAX = 1024;
+struct Tracer {
+  long long* buf;
+  int n;
+  __device__ __forceinline__ void init(long long* base, int warp) {
+    buf = (base != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? base + (size_t)warp * TRACE_MAX : nullptr;
+    n = 0;
+  }
+  __device__ __forceinline__ void ev(int id) {
+    if (buf != nullptr && n < TRACE_MAX) buf[n++] = ((long long)id << 48) | (clock64() & 0xFFFFFFFFFFFFLL);
+  }
 };
 
 // =====================================================================================================================
@@ -151,13 +170,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_fwd_tc_kernel(const __grid_c
   const uint32_t q_bytes = (uint32_t)qrows * ROWB, kv_bytes = (uint32_t)p.Npad * ROWB;
   const uint32_t stage_bytes = q_bytes + 2 * kv_bytes;
   FwdBars* bars = reinterpret_cast<FwdBars*>(smem + F_NST * stage_bytes);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int C = p.heads * HD;
   const int my_units = ((int)blockIdx.x < p.units) ? (p.units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   // item i of slot s:  two query tiles per head -> head i, tile (i + s) & 1;  one tile -> head 2 i + s, tile 0
   const int two = (p.ntq == 2);
   const int nch = p.Npad >> 4;                       // 16-key chunks
   const int h0 = (nch + 1) >> 1;                     // chunks [0, h0) belong to column half 0, [h0, nch) to half 1
+  Tracer tr;
+  tr.init(p.trace, warp);
 
   if (tid == 0) {
     for (int s = 0; s < F_NST; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
@@ -177,25 +198,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_fwd_tc_kernel(const __grid_c
   constexpr uint32_t SLOT = 256, O_COL = 224;
 
   if (warp == W_TMA) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
+    {
+      const bool leader = elect_one();
       for (int ul = 0; ul < my_units; ++ul) {
         const int st = ul % F_NST;
         mbar_wait(&bars->empty[st], ((ul / F_NST) & 1) ^ 1);
         const int unit = blockIdx.x + ul * gridDim.x;
         const int b = unit / p.heads, hd = unit % p.heads;
         uint8_t* sq = smem + st * stage_bytes;
-        mbar_expect_tx(&bars->full[st], stage_bytes);
-        tma_load_2d(sq, &map_q, &bars->full[st], hd * HD, b * p.N);
-        tma_load_2d(sq + q_bytes, &map_kv, &bars->full[st], C + hd * HD, b * p.N);
-        tma_load_2d(sq + q_bytes + kv_bytes, &map_kv, &bars->full[st], 2 * C + hd * HD, b * p.N);
+        if (leader) {
+          mbar_expect_tx(&bars->full[st], stage_bytes);
+          tma_load_2d(sq, &map_q, &bars->full[st], hd * HD, b * p.N);
+          tma_load_2d(sq + q_bytes, &map_kv, &bars->full[st], C + hd * HD, b * p.N);
+          tma_load_2d(sq + q_bytes + kv_bytes, &map_kv, &bars->full[st], 2 * C + hd * HD, b * p.N);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == W_MMA) {
     // ===================== MMA issuer: polls the two slots =====================
     // One thread feeds the tensor pipe for the whole SM, so its instruction stream is kept short: item cursors advance
     // incrementally (no divisions) and the shared-memory descriptors are built once per item and stepped by constants.
-    if (lane == 0) {
+    // The WHOLE warp runs this loop with warp-uniform state; only the tcgen05 instructions sit under the elected lane.
+    {
+      const bool leader = elect_one();
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_slot, 0);
       const uint32_t idS = idesc_mn(QT, p.Npad, 0, 0), idO = idesc_mn(QT, HD, 0, 1);
       const uint32_t smem_a = smem_u32(smem);
       int n_items[2], s_issued[2] = {0, 0}, pv_issued[2] = {0, 0};
@@ -214,14 +242,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_fwd_tc_kernel(const __grid_c
         for (int s = 0; s < 2; ++s) {
           // ---- S of the slot's next item: the slot is free once the P V product of its previous item has been issued
           if (s_issued[s] < n_items[s] && s_issued[s] == pv_issued[s]) {
-            if (mbar_test(&bars->full[s_st[s]], (uint32_t)s_ph[s])) {
+            if (mbar_test_u(&bars->full[s_st[s]], (uint32_t)s_ph[s])) {
               fence_after();
               const int qt = two ? ((s_issued[s] + s) & 1) : 0;
               const uint32_t base = smem_a + (uint32_t)s_st[s] * stage_bytes;
               const uint64_t qd = desc64(base + (uint32_t)qt * QT * ROWB, 16), kd = desc64(base + q_bytes, 16);
-              umma_bf16(tmem_base + s * SLOT, qd, kd, idS, 0u);
-              umma_bf16(tmem_base + s * SLOT, qd + 2, kd + 2, idS, 1u);       // + 32 B = next 16 channels
-              umma_commit(&bars->s_ready[s]);
+              tr.ev(20 + s);
+              if (leader) {
+                umma_bf16(tmem_base + s * SLOT, qd, kd, idS, 0u);
+                umma_bf16(tmem_base + s * SLOT, qd + 2, kd + 2, idS, 1u);       // + 32 B = next 16 channels
+                umma_commit(&bars->s_ready[s]);
+              }
+              __syncwarp();
               ++s_issued[s];
               for (int k = 0; k < ul_step; ++k) {                             // advance the S cursor
                 ++s_ul[s];
@@ -230,28 +262,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_fwd_tc_kernel(const __grid_c
             }
           }
           // ---- O = P V once both column halves have stored their P
-          if (pv_issued[s] < s_issued[s] && mbar_test(&bars->p_ready[s], pv_issued[s] & 1)) {
+          if (pv_issued[s] < s_issued[s] && mbar_test_u(&bars->p_ready[s], pv_issued[s] & 1)) {
             fence_after();
             const int st = v_st[s];
-            uint64_t vd = desc64(smem_a + (uint32_t)st * stage_bytes + q_bytes + kv_bytes, 16);
+            const uint64_t vd0 = desc64(smem_a + (uint32_t)st * stage_bytes + q_bytes + kv_bytes, 16);
             const uint32_t to = tmem_base + s * SLOT + O_COL;
-            uint32_t pa = tmem_base + s * SLOT;
-            // P of chunk kk: half 0 packs chunk c at columns 8c, half 1 at 16 h0 + 8 (c - h0) (inside its own S columns)
-            umma_ts(to, pa, vd, idO, 0u);
-            for (int kk = 1; kk < h0; ++kk) {
-              pa += 8; vd += (16 * ROWB) >> 4;
-              umma_ts(to, pa, vd, idO, 1u);
+            const uint32_t pa0 = tmem_base + s * SLOT, pa1 = pa0 + 16 * h0 - 8 * h0;
+            const bool last_of_head = ++pv_of_stage[st] == p.ntq;   // every product reading this head's tiles has been issued
+            if (last_of_head) pv_of_stage[st] = 0;
+            tr.ev(30 + s);
+            if (leader) {
+              // P of chunk kk: half 0 packs chunk c at columns 8c, half 1 at 16 h0 + 8 (c - h0) (inside its own S columns)
+              umma_ts(to, pa0, vd0, idO, 0u);
+              for (int kk = 1; kk < h0; ++kk) umma_ts(to, pa0 + 8 * kk, vd0 + (uint64_t)(kk * ((16 * ROWB) >> 4)), idO, 1u);
+              for (int kk = h0; kk < nch; ++kk) umma_ts(to, pa1 + 8 * kk, vd0 + (uint64_t)(kk * ((16 * ROWB) >> 4)), idO, 1u);
+              umma_commit(&bars->o_ready[s]);
+              if (last_of_head) umma_commit(&bars->empty[st]);
             }
-            pa = tmem_base + s * SLOT + 16 * h0 - 8;
-            for (int kk = h0; kk < nch; ++kk) {
-              pa += 8; vd += (16 * ROWB) >> 4;
-              umma_ts(to, pa, vd, idO, 1u);
-            }
-            umma_commit(&bars->o_ready[s]);
-            if (++pv_of_stage[st] == p.ntq) {          // every product reading this head's tiles has been issued
-              pv_of_stage[st] = 0;
-              umma_commit(&bars->empty[st]);
-            }
+            __syncwarp();
+            tr.ev(40 + s);
             ++pv_issued[s];
             for (int k = 0; k < ul_step; ++k)
               if (++v_st[s] == F_NST) v_st[s] = 0;
@@ -274,8 +303,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_fwd_tc_kernel(const __grid_c
       const int b = unit / p.heads, hd = unit % p.heads;
       const int row = qt * QT + t;
       const bool warp_live = (qt * QT + (warp & 3) * 32) < N;      // warp-uniform: any valid row in this warp
+      tr.ev(1);
       mbar_wait(&bars->s_ready[s], i & 1);
       fence_after();
+      tr.ev(2);
       float m = -INFINITY, l = 0.f;
       uint32_t ra[16], rb[16];
       if (warp_live && c_lo < c_hi) {
@@ -307,7 +338,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_fwd_tc_kernel(const __grid_c
         m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
       bars->xm[s][hf][t] = m;
+      tr.ev(3);
       bar_sync(1 + s, 256);                            // the two column halves of this slot
+      tr.ev(4);
       m = fmaxf(m, bars->xm[s][hf ^ 1][t]);
       if (warp_live && c_lo < c_hi) {
         // ---- pass 2: P = exp2((S - m) * scale * log2e) -> packed bf16 over S columns this thread has consumed
@@ -353,9 +386,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_fwd_tc_kernel(const __grid_c
       }
       bars->xl[s][hf][t] = l;
       fence_before();
+      tr.ev(5);
       mbar_arrive(&bars->p_ready[s]);
       mbar_wait(&bars->o_ready[s], i & 1);
       fence_after();
+      tr.ev(6);
       if (warp_live) {
         // ---- epilogue: this half normalises and stores 16 of the 32 output channels
         tmem_ld16(lane_addr + O_COL + (uint32_t)(hf * 16), ra);
@@ -420,11 +455,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
   const uint32_t stage_bytes = 2 * q_bytes + 2 * kv_bytes;
   uint8_t* stages = smem + 4 * PBUF;
   BwdBars* bars = reinterpret_cast<BwdBars*>(stages + B_NST * stage_bytes);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int C = p.heads * HD, N = p.N;
   const int my_units = ((int)blockIdx.x < p.units) ? (p.units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int nkb = (p.Npad + KB - 1) / KB;
   const int ntq = p.ntq;
+  Tracer tr;
+  tr.init(p.trace, warp);
   // items of a head in issue order: e = kb * ntq + qt.  Slot of item e of CTA-local head ul: two query tiles ->
   // qt ^ (ul & 1) (a slot alternates between the full and the partial tile); one tile -> kb & 1 (slots alternate key blocks)
 
@@ -450,19 +487,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
   const uint32_t tmem_base = bars->tmem_slot;
 
   if (warp == W_TMA) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
+    {
+      const bool leader = elect_one();
       for (int ul = 0; ul < my_units; ++ul) {
         const int st = ul % B_NST;
         mbar_wait(&bars->empty[st], ((ul / B_NST) & 1) ^ 1);
         const int unit = blockIdx.x + ul * gridDim.x;
         const int b = unit / p.heads, hd = unit % p.heads;
         uint8_t* sq = stages + st * stage_bytes;
-        mbar_expect_tx(&bars->full[st], stage_bytes);
-        tma_load_2d(sq, &map_q, &bars->full[st], hd * HD, b * N);
-        tma_load_2d(sq + q_bytes, &map_do, &bars->full[st], hd * HD, b * N);
-        tma_load_2d(sq + 2 * q_bytes, &map_kv, &bars->full[st], C + hd * HD, b * N);
-        tma_load_2d(sq + 2 * q_bytes + kv_bytes, &map_kv, &bars->full[st], 2 * C + hd * HD, b * N);
+        if (leader) {
+          mbar_expect_tx(&bars->full[st], stage_bytes);
+          tma_load_2d(sq, &map_q, &bars->full[st], hd * HD, b * N);
+          tma_load_2d(sq + q_bytes, &map_do, &bars->full[st], hd * HD, b * N);
+          tma_load_2d(sq + 2 * q_bytes, &map_kv, &bars->full[st], C + hd * HD, b * N);
+          tma_load_2d(sq + 2 * q_bytes + kv_bytes, &map_kv, &bars->full[st], 2 * C + hd * HD, b * N);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == W_MMA) {
@@ -470,7 +511,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
     // One thread feeds the tensor pipe for the whole SM: item cursors advance incrementally (no divisions), descriptors
     // are built once per item and stepped by constants, and at every hand-over the NEXT item's S / dP products go out
     // before the current item's dV / dK / dQ products, so the slot's warpgroups resume while those still run.
-    if (lane == 0) {
+    // The WHOLE warp runs this loop with warp-uniform state; only the tcgen05 instructions sit under the elected lane.
+    {
+      const bool leader = elect_one();
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_slot, 0);
       const int items_per_unit = ntq * nkb;
       const uint32_t smem_a = smem_u32(smem), stages_a = smem_u32(stages);
       const uint32_t idT = idesc_mn(QT, HD, 1, 1);        // dV / dK: A = P^T / dS^T (MN-major), B = dO / Q (MN-major)
@@ -505,19 +549,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
       const uint64_t dsd_[2] = {desc64(smem_a + PBUF, QT * ROWB), desc64(smem_a + 3 * PBUF, QT * ROWB)};          // dS^T (MN-major A)
       auto issue_sdp = [&](int s) -> bool {
         const Cur& c = sd[s];
-        if (!mbar_test(&bars->full[c.st], (uint32_t)c.ph)) return false;
+        if (!mbar_test_u(&bars->full[c.st], (uint32_t)c.ph)) return false;
         fence_after();
+        tr.ev(20 + s);
         const uint32_t sq = stages_a + (uint32_t)c.st * stage_bytes, sdo = sq + q_bytes, sk = sdo + q_bytes, sv = sk + kv_bytes;
         const int kw = min(KB, p.Npad - c.kb * KB);
         const uint32_t id = idesc_mn(QT, kw, 0, 0);
         const uint32_t ts = tmem_base + s * B_SLOT;
         const uint64_t qd = desc64(sq + (uint32_t)c.qt * QT * ROWB, 16), kd = desc64(sk + (uint32_t)c.kb * KB * ROWB, 16);
         const uint64_t od = desc64(sdo + (uint32_t)c.qt * QT * ROWB, 16), vd = desc64(sv + (uint32_t)c.kb * KB * ROWB, 16);
-        umma_bf16(ts, qd, kd, id, 0u);
-        umma_bf16(ts, qd + 2, kd + 2, id, 1u);
-        umma_bf16(ts + KB, od, vd, id, 0u);
-        umma_bf16(ts + KB, od + 2, vd + 2, id, 1u);
-        umma_commit(&bars->sdp_ready[s]);
+        if (leader) {
+          umma_bf16(ts, qd, kd, id, 0u);
+          umma_bf16(ts, qd + 2, kd + 2, id, 1u);
+          umma_bf16(ts + KB, od, vd, id, 0u);
+          umma_bf16(ts + KB, od + 2, vd + 2, id, 1u);
+          umma_commit(&bars->sdp_ready[s]);
+        }
+        __syncwarp();
         cur_next(sd[s], s);
         sdp_pending[s] = sd[s].valid;
         return true;
@@ -531,7 +579,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           // has the slot stored P / dS of its current item?  (never before that item's S / dP were issued)
-          if (mm[s].valid && !prod_ready[s] && n_sdp[s] > n_mma[s] && mbar_test(&bars->pds_ready[s], n_mma[s] & 1)) prod_ready[s] = true;
+          if (mm[s].valid && !prod_ready[s] && n_sdp[s] > n_mma[s] && mbar_test_u(&bars->pds_ready[s], n_mma[s] & 1)) prod_ready[s] = true;
           // S / dP of the slot's next item: allowed when the slot is idle, or at the hand-over (the warpgroups drained the
           // S / dP accumulators before they arrived on pds_ready) -- then it goes out BEFORE the current item's products
           if (sdp_pending[s] && (n_sdp[s] == n_mma[s] || (n_sdp[s] == n_mma[s] + 1 && prod_ready[s]))) {
@@ -541,10 +589,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
           const Cur c = mm[s];
           const int gkb = c.ul * nkb + c.kb, j = gkb & 1;            // global key-block counter -> accumulator buffer
           // first contribution to this key block: its accumulator buffer must have been stored (two blocks ago)
-          if (contrib_of[gkb & 3] == 0 && gkb >= 2 && !mbar_test(&bars->dkv_free[j], ((gkb >> 1) - 1) & 1)) continue;
+          if (contrib_of[gkb & 3] == 0 && gkb >= 2 && !mbar_test_u(&bars->dkv_free[j], ((gkb >> 1) - 1) & 1)) continue;
           // first contribution to dQ of this query tile in this head: the previous head's dQ must have been stored
           const bool dq_first = dq_unit[c.qt] != c.ul;
-          if (dq_first && c.ul > 0 && !mbar_test(&bars->dq_free[c.qt], (c.ul - 1) & 1)) continue;
+          if (dq_first && c.ul > 0 && !mbar_test_u(&bars->dq_free[c.qt], (c.ul - 1) & 1)) continue;
           fence_after();
           {
             const uint32_t sq = stages_a + (uint32_t)c.st * stage_bytes, sdo = sq + q_bytes, sk = sdo + q_bytes;
@@ -552,34 +600,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
             const uint32_t tdk = tmem_base + B_DKV + 64 * j, tdv = tdk + 32;
             const uint32_t acc0 = contrib_of[gkb & 3] > 0 ? 1u : 0u;
             const uint64_t dod = desc64(sdo + (uint32_t)c.qt * QT * ROWB, 16), qd = desc64(sq + (uint32_t)c.qt * QT * ROWB, 16);
-            // dV_b += P^T dO ; dK_b += dS^T Q : K = the 128 query rows of this tile (8 k-steps of 16 rows = 1024 B)
-            umma_bf16(tdv, pd_[s], dod, idT, acc0);
-#pragma unroll
-            for (int kk = 1; kk < QT / 16; ++kk) umma_bf16(tdv, pd_[s] + kk * 64, dod + kk * 64, idT, 1u);
-            umma_bf16(tdk, dsd_[s], qd, idT, acc0);
-#pragma unroll
-            for (int kk = 1; kk < QT / 16; ++kk) umma_bf16(tdk, dsd_[s] + kk * 64, qd + kk * 64, idT, 1u);
-            // dQ_qt += dS K_b : K = the keys of this block (kw / 16 k-steps; 16 keys = half a 32-key block = 32 B)
             const uint64_t dsk = desc64(smem_a + (2 * s + 1) * PBUF, 16);
-            uint64_t kd = desc64(sk + (uint32_t)(c.kb * KB) * ROWB, 16);
+            const uint64_t kd0 = desc64(sk + (uint32_t)(c.kb * KB) * ROWB, 16);
             const uint32_t tdq = tmem_base + B_DQ + c.qt * 32;
             const int nk = kw >> 4;
-            umma_bf16(tdq, dsk, kd, idQ, dq_first ? 0u : 1u);
-            for (int kk = 1; kk < nk; ++kk) {
-              kd += (16 * ROWB) >> 4;
-              umma_bf16(tdq, dsk + (uint64_t)((kk >> 1) * ((QT * ROWB) >> 4) + (kk & 1) * 2), kd, idQ, 1u);
-            }
-            umma_commit(&bars->mma_done[s]);
-            if (++contrib_of[gkb & 3] == ntq) {              // dK_b / dV_b complete once these products retire
-              contrib_of[gkb & 3] = 0;
-              umma_commit(&bars->dkv_ready[j]);
-            }
+            const bool dkv_complete = ++contrib_of[gkb & 3] == ntq;      // dK_b / dV_b complete once these products retire
+            if (dkv_complete) contrib_of[gkb & 3] = 0;
             if (dq_first) { dq_unit[c.qt] = c.ul; dq_cnt[c.qt] = 0; }
-            if (++dq_cnt[c.qt] == nkb) umma_commit(&bars->dq_ready[c.qt]);
-            if (++done_in_stage[c.st] == items_per_unit) {     // every product reading this head's tiles has been issued
-              done_in_stage[c.st] = 0;
-              umma_commit(&bars->empty[c.st]);
+            const bool dq_complete = ++dq_cnt[c.qt] == nkb;
+            const bool head_done = ++done_in_stage[c.st] == items_per_unit;   // every product reading this head's tiles issued
+            if (head_done) done_in_stage[c.st] = 0;
+            tr.ev(30 + s);
+            if (leader) {
+              // dV_b += P^T dO ; dK_b += dS^T Q : K = the 128 query rows of this tile (8 k-steps of 16 rows = 1024 B)
+              umma_bf16(tdv, pd_[s], dod, idT, acc0);
+#pragma unroll
+              for (int kk = 1; kk < QT / 16; ++kk) umma_bf16(tdv, pd_[s] + kk * 64, dod + kk * 64, idT, 1u);
+              umma_bf16(tdk, dsd_[s], qd, idT, acc0);
+#pragma unroll
+              for (int kk = 1; kk < QT / 16; ++kk) umma_bf16(tdk, dsd_[s] + kk * 64, qd + kk * 64, idT, 1u);
+              // dQ_qt += dS K_b : K = the keys of this block (kw / 16 k-steps; 16 keys = half a 32-key block = 32 B)
+              umma_bf16(tdq, dsk, kd0, idQ, dq_first ? 0u : 1u);
+              for (int kk = 1; kk < nk; ++kk)
+                umma_bf16(tdq, dsk + (uint64_t)((kk >> 1) * ((QT * ROWB) >> 4) + (kk & 1) * 2), kd0 + (uint64_t)(kk * ((16 * ROWB) >> 4)), idQ, 1u);
+              umma_commit(&bars->mma_done[s]);
+              if (dkv_complete) umma_commit(&bars->dkv_ready[j]);
+              if (dq_complete) umma_commit(&bars->dq_ready[c.qt]);
+              if (head_done) umma_commit(&bars->empty[c.st]);
             }
+            __syncwarp();
+            tr.ev(40 + s);
           }
           ++n_mma[s];
           prod_ready[s] = false;
@@ -597,58 +647,74 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
     const float sl2 = p.scale * 1.4426950408889634f;
     const uint32_t sp = smem_u32(smem + (2 * s) * PBUF), sds = sp + PBUF;
     uint32_t n_item = 0;          // items this slot has processed (parity source of sdp_ready / mma_done)
-    auto row_ptr = [&](const bf16* base, int b, int row, int hd) { return base + ((size_t)b * N + row) * C + (size_t)hd * HD; };
-    for (int ul = 0; ul < my_units; ++ul) {
+    // per-row constants of a head: lse (log2 units) and D = sum_d dO * O (backward of models/volo.py:193-197:
+    // dS = P (dP - D)); D comes from the row-dot pre-pass ([B, heads, N] like lse), both are fetched ONE HEAD AHEAD
+    auto load_consts = [&](int ul, float& lse2, float& Dr) {
+      lse2 = 0.f; Dr = 0.f;
+      if (ul >= my_units) return;
       const int unit = blockIdx.x + ul * gridDim.x;
-      const int b = unit / p.heads, hd = unit % p.heads;
-      const int qt = (ntq == 2) ? (s ^ (ul & 1)) : 0;          // the query tile this slot works on in this head
+      const int qt = (ntq == 2) ? (s ^ (ul & 1)) : 0;
       const int row = qt * QT + t;
-      const bool row_ok = row < N;
-      const bool warp_live = (qt * QT + (warp & 3) * 32) < N;
-      // warm the caches for the NEXT head's per-row constants (this head's were prefetched one head ago)
-      if (ul + 1 < my_units) {
-        const int un = unit + gridDim.x, bn = un / p.heads, hn = un % p.heads;
-        const int qn = (ntq == 2) ? (s ^ ((ul + 1) & 1)) : 0, rn = qn * QT + t;
-        if (rn < N && hf == 0) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(row_ptr(p.o, bn, rn, hn)));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(row_ptr(p.dout, bn, rn, hn)));
-        }
+      if (row < N) {
+        const size_t off = (size_t)unit * N + row;            // unit = b * heads + hd
+        lse2 = __ldg(p.lse + off) * 1.4426950408889634f;
+        Dr = __ldg(p.rowdot + off);
       }
-      // per-row constants: lse (log2 units) and D = sum_d dO * O  (backward of models/volo.py:193-197: dS = P (dP - D))
-      float lse2 = 0.f, Dr = 0.f;
-      if (row_ok) {
-        lse2 = p.lse[((size_t)b * p.heads + hd) * N + row] * 1.4426950408889634f;
-        const uint4* po = reinterpret_cast<const uint4*>(row_ptr(p.o, b, row, hd));
-        const uint4* pd = reinterpret_cast<const uint4*>(row_ptr(p.dout, b, row, hd));
+    };
+    // dK (warpgroups with hf == 0) / dV (hf == 1) of global key block gkb: lanes = its keys; slot s stores channels [16 s, +16)
+    auto store_dkv = [&](int unit, int kb, int gkb) {
+      const int b = unit / p.heads, hd = unit % p.heads;
+      const int j = gkb & 1;
+      const int k0 = kb * KB, kw = min(KB, p.Npad - k0);
+      tr.ev(6);
+      mbar_wait(&bars->dkv_ready[j], (gkb >> 1) & 1);
+      fence_after();
+      tr.ev(7);
+      const bool key_live = (k0 + (warp & 3) * 32) < min(N, k0 + kw);      // warp-uniform
+      if (key_live) {
+        uint32_t o[16];
+        tmem_ld16(lane_base + B_DKV + 64 * j + 32 * hf + 16 * s, o);
+        wait_ld();
+        pin16(o);
+        const int key = k0 + t;
+        if (t < kw && key < N) {
+          const float f = (hf == 0) ? p.scale : 1.f;
+          bf16* dst = p.out + ((size_t)b * N + key) * 3 * C + (size_t)(1 + hf) * C + (size_t)hd * HD + 16 * s;
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const uint4 a = __ldg(po + c4), d = __ldg(pd + c4);
-          const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
-          const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&d);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 fa = __bfloat1622float2(ha[i]), fb = __bfloat1622float2(hb[i]);
-            Dr = fmaf(fa.x, fb.x, Dr);
-            Dr = fmaf(fa.y, fb.y, Dr);
+          for (int c4 = 0; c4 < 2; ++c4) {
+            uint4 pkv;
+            pkv.x = pack2(__uint_as_float(o[c4 * 8 + 0]) * f, __uint_as_float(o[c4 * 8 + 1]) * f);
+            pkv.y = pack2(__uint_as_float(o[c4 * 8 + 2]) * f, __uint_as_float(o[c4 * 8 + 3]) * f);
+            pkv.z = pack2(__uint_as_float(o[c4 * 8 + 4]) * f, __uint_as_float(o[c4 * 8 + 5]) * f);
+            pkv.w = pack2(__uint_as_float(o[c4 * 8 + 6]) * f, __uint_as_float(o[c4 * 8 + 7]) * f);
+            *reinterpret_cast<uint4*>(dst + c4 * 8) = pkv;
           }
         }
       }
-      // dK (warpgroups with hf == 0) / dV (hf == 1) of global key block gkb: lanes = its keys; slot s stores channels [16 s, +16)
-      auto store_dkv = [&](int kb) {
-        const int gkb = ul * nkb + kb, j = gkb & 1;
-        const int k0 = kb * KB, kw = min(KB, p.Npad - k0);
-        mbar_wait(&bars->dkv_ready[j], (gkb >> 1) & 1);
+      fence_before();
+      tr.ev(8);
+      mbar_arrive(&bars->dkv_free[j]);
+    };
+    // dQ of the query tiles of CTA-local head ul: stored by the slot that owns item (qq, 0); halves store 16 channels each
+    auto store_dq = [&](int ul) {
+      const int unit = blockIdx.x + ul * gridDim.x;
+      const int b = unit / p.heads, hd = unit % p.heads;
+      for (int qq = 0; qq < ntq; ++qq) {
+        const int owner = (ntq == 2) ? (qq ^ (ul & 1)) : 0;
+        if (owner != s) continue;
+        tr.ev(9);
+        mbar_wait(&bars->dq_ready[qq], ul & 1);
         fence_after();
-        const bool key_live = (k0 + (warp & 3) * 32) < min(N, k0 + kw);      // warp-uniform
-        if (key_live) {
+        tr.ev(10);
+        const int rowq = qq * QT + t;
+        if ((qq * QT + (warp & 3) * 32) < N) {
           uint32_t o[16];
-          tmem_ld16(lane_base + B_DKV + 64 * j + 32 * hf + 16 * s, o);
+          tmem_ld16(lane_base + B_DQ + qq * 32 + 16 * hf, o);
           wait_ld();
           pin16(o);
-          const int key = k0 + t;
-          if (t < kw && key < N) {
-            const float f = (hf == 0) ? p.scale : 1.f;
-            bf16* dst = p.out + ((size_t)b * N + key) * 3 * C + (size_t)(1 + hf) * C + (size_t)hd * HD + 16 * s;
+          if (rowq < N) {
+            bf16* dst = p.out + ((size_t)b * N + rowq) * 3 * C + (size_t)hd * HD + 16 * hf;
+            const float f = p.scale;
 #pragma unroll
             for (int c4 = 0; c4 < 2; ++c4) {
               uint4 pkv;
@@ -661,16 +727,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
           }
         }
         fence_before();
-        mbar_arrive(&bars->dkv_free[j]);
-      };
+        mbar_arrive(&bars->dq_free[qq]);
+      }
+    };
+    float lse2, Dr, lse2_n, Dr_n;
+    load_consts(0, lse2, Dr);
+    // stores run one step LATE (also across heads): the products of a key block / a head retire while the next item is
+    // being computed, so nobody waits for the tensor pipe
+    int pend_unit = -1, pend_kb = 0, pend_gkb = 0, pend_dq_ul = -1;
+    for (int ul = 0; ul < my_units; ++ul) {
+      const int unit = blockIdx.x + ul * gridDim.x;
+      const int qt = (ntq == 2) ? (s ^ (ul & 1)) : 0;          // the query tile this slot works on in this head
+      const int row = qt * QT + t;
+      const bool row_ok = row < N;
+      const bool warp_live = (qt * QT + (warp & 3) * 32) < N;
+      load_consts(ul + 1, lse2_n, Dr_n);
       for (int kb = 0; kb < nkb; ++kb) {
         const bool mine = (ntq == 2) || ((kb & 1) == s);       // does this slot own item (qt, kb)?
         if (mine) {
           const int k0 = kb * KB, kw = min(KB, p.Npad - k0);
           const int nch = kw >> 4, h0 = (nch + 1) >> 1;
           const int c_lo = hf ? h0 : 0, c_hi = hf ? nch : h0;
+          tr.ev(1);
           mbar_wait(&bars->sdp_ready[s], n_item & 1);
           fence_after();
+          tr.ev(2);
           // (the previous item's products must have read P / dS before they are overwritten: waited for right before the
           //  first shared-memory store, so the TMEM loads and the exponentials of the first chunk overlap those products)
           const bool wait_prev = n_item > 0;
@@ -699,7 +780,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
               // keys [16c, 16c+16) of this block -> 32-key block (c >> 1), 16-byte chunks 2 (c & 1) and 2 (c & 1) + 1 of row t
               const uint32_t blk = (uint32_t)(c >> 1) * (QT * ROWB);
               const int c0 = (c & 1) * 2;
-              if (c == c_lo && wait_prev) mbar_wait(&bars->mma_done[s], prev_par);
+              if (c == c_lo && wait_prev) { tr.ev(3); mbar_wait(&bars->mma_done[s], prev_par); tr.ev(4); }
               sts128(sp + blk + sw64(t, c0), pk[0], pk[1], pk[2], pk[3]);
               sts128(sp + blk + sw64(t, c0 + 1), pk[4], pk[5], pk[6], pk[7]);
               sts128(sds + blk + sw64(t, c0), dk[0], dk[1], dk[2], dk[3]);
@@ -719,42 +800,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the MMAs
           fence_before();
+          tr.ev(5);
           mbar_arrive(&bars->pds_ready[s]);
           ++n_item;
         }
-        if (kb > 0) store_dkv(kb - 1);        // one key block late: its products retired while this block was computed
+        // late stores: the previous head's dQ (once, after this head's first item) and the previous key block's dK / dV
+        if (pend_dq_ul >= 0) { store_dq(pend_dq_ul); pend_dq_ul = -1; }
+        if (pend_unit >= 0) store_dkv(pend_unit, pend_kb, pend_gkb);
+        pend_unit = unit; pend_kb = kb; pend_gkb = ul * nkb + kb;
       }
-      store_dkv(nkb - 1);
-      // ---- dQ of query tile qq: stored by the slot that owns item (qq, 0); the two halves store 16 channels each
-      for (int qq = 0; qq < ntq; ++qq) {
-        const int owner = (ntq == 2) ? (qq ^ (ul & 1)) : 0;
-        if (owner != s) continue;
-        mbar_wait(&bars->dq_ready[qq], ul & 1);
-        fence_after();
-        const int rowq = qq * QT + t;
-        if ((qq * QT + (warp & 3) * 32) < N) {
-          uint32_t o[16];
-          tmem_ld16(lane_base + B_DQ + qq * 32 + 16 * hf, o);
-          wait_ld();
-          pin16(o);
-          if (rowq < N) {
-            bf16* dst = p.out + ((size_t)b * N + rowq) * 3 * C + (size_t)hd * HD + 16 * hf;
-            const float f = p.scale;
-#pragma unroll
-            for (int c4 = 0; c4 < 2; ++c4) {
-              uint4 pkv;
-              pkv.x = pack2(__uint_as_float(o[c4 * 8 + 0]) * f, __uint_as_float(o[c4 * 8 + 1]) * f);
-              pkv.y = pack2(__uint_as_float(o[c4 * 8 + 2]) * f, __uint_as_float(o[c4 * 8 + 3]) * f);
-              pkv.z = pack2(__uint_as_float(o[c4 * 8 + 4]) * f, __uint_as_float(o[c4 * 8 + 5]) * f);
-              pkv.w = pack2(__uint_as_float(o[c4 * 8 + 6]) * f, __uint_as_float(o[c4 * 8 + 7]) * f);
-              *reinterpret_cast<uint4*>(dst + c4 * 8) = pkv;
-            }
-          }
-        }
-        fence_before();
-        mbar_arrive(&bars->dq_free[qq]);
-      }
+      pend_dq_ul = ul;
+      lse2 = lse2_n; Dr = Dr_n;
     }
+    if (pend_unit >= 0) store_dkv(pend_unit, pend_kb, pend_gkb);
+    if (pend_dq_ul >= 0) store_dq(pend_dq_ul);
   }
   fence_before();
   __syncthreads();
@@ -762,6 +821,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+}
+
+// D[b, h, n] = sum_d dO[b, n, h, d] * O[b, n, h, d]  (fp32): one thread per (b, n, h), 64 B of each operand; consecutive
+// threads take consecutive heads, so a warp reads 2 KB contiguous per tensor.  Output in the [B, heads, N] layout of lse.
+__global__ void __launch_bounds__(256) mhsa_rowdot_tc_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout,
+                                                             float* __restrict__ D, long long total, int N, int heads) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;      // (b * N + n) * heads + h
+  if (i >= total) return;
+  const uint4* po = reinterpret_cast<const uint4*>(o + i * HD);
+  const uint4* pd = reinterpret_cast<const uint4*>(dout + i * HD);
+  float acc = 0.f;
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    const uint4 a = __ldg(po + c4), d = __ldg(pd + c4);
+    const __nv_bfloat162* ha = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = __bfloat1622float2(ha[k]), fb = __bfloat1622float2(hb[k]);
+      acc = fmaf(fa.x, fb.x, acc);
+      acc = fmaf(fa.y, fb.y, acc);
+    }
+  }
+  const int h = (int)(i % heads);
+  const long long bn = i / heads;
+  const int n = (int)(bn % N);
+  const long long b = bn / N;
+  D[(b * heads + h) * N + n] = acc;
 }
 
 // 2-D bf16 tensor [rows, cols] row-major, box {32 channels (64 B), box_rows}, 64B swizzle, zero fill outside the tensor
@@ -787,6 +874,7 @@ bool tc_envelope(const void* a, const void* b, int B, int N, int heads, int D) {
 }
 
 std::mutex g_attr_mu;
+long long* g_trace = nullptr;
 
 }  // namespace
 
@@ -799,6 +887,7 @@ int apb_mhsa_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int he
   p.Npad = (N + 15) / 16 * 16;
   p.ntq = (N + QT - 1) / QT;
   p.units = B * heads;
+  p.trace = g_trace;
   const int C = heads * HD;
   CUtensorMap mq, mkv;
   int rc = make_map64(&mq, qkv, (long long)B * N, 3LL * C, p.ntq * QT);
@@ -821,16 +910,19 @@ int apb_mhsa_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int he
   return 0;
 }
 
-int apb_mhsa_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int N, int heads,
-                    int D, float scale, apb_stream_t stream) {
+int apb_mhsa_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace, int B,
+                    int N, int heads, int D, float scale, apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
   if (!tc_envelope(qkv, dqkv, B, N, heads, D) || (((uintptr_t)out | (uintptr_t)dout) & 15) != 0) return APB_ERR_UNSUPPORTED;
+  APB_CHECK_ARG(workspace != nullptr, APB_ERR_ARG, "mhsa_bwd_tc: workspace of B*heads*N floats required");
   AttParams p{};
   p.qkv = (const bf16*)qkv; p.o = (const bf16*)out; p.dout = (const bf16*)dout; p.out = (bf16*)dqkv; p.lse = const_cast<float*>(lse);
+  p.rowdot = workspace;
   p.B = B; p.N = N; p.heads = heads; p.scale = scale;
   p.Npad = (N + 15) / 16 * 16;
   p.ntq = (N + QT - 1) / QT;
   p.units = B * heads;
+  p.trace = g_trace;
   const int C = heads * HD;
   CUtensorMap mq, mkv, mdo;
   int rc = make_map64(&mq, qkv, (long long)B * N, 3LL * C, p.ntq * QT);
@@ -850,8 +942,19 @@ int apb_mhsa_bwd_tc(const void* qkv, const void* out, const void* dout, const fl
       attr = smem;
     }
   }
+  {
+    const long long total = (long long)B * N * heads;
+    mhsa_rowdot_tc_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const bf16*)out, (const bf16*)dout, workspace, total, N, heads);
+    APB_LAUNCH_CHECK("mhsa_rowdot_tc");
+  }
   const int grid = p.units < num_sms() ? p.units : num_sms();
   mhsa_bwd_tc_kernel<<<grid, NTHREADS, smem, st>>>(mq, mkv, mdo, p);
   APB_LAUNCH_CHECK("mhsa_bwd_tc");
+  return 0;
+}
+
+// diagnostic: device buffer of 18 * 1024 int64 that CTA 0 of the next attention launches fills with (event, clock) pairs
+extern "C" int apb_debug_mhsa_trace(long long* buf) {
+  g_trace = buf;
   return 0;
 }

@@ -50,7 +50,7 @@ int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads
 int apb_mhsa_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace,
                  int B, int N, int heads, int D, float scale, int dtype, apb_stream_t stream) {
   if (dtype == APB_BF16 && D == 32 && B > 0 && N > 0 && N <= 224 && heads > 0) {
-    const int rc = apb_mhsa_bwd_tc(qkv, out, dout, lse, dqkv, B, N, heads, D, scale, stream);
+    const int rc = apb_mhsa_bwd_tc(qkv, out, dout, lse, dqkv, workspace, B, N, heads, D, scale, stream);
     if (rc != APB_ERR_UNSUPPORTED) return rc;
   }
   if (dtype == APB_BF16 && (D == 32 || D == 64) && B > 0 && N > 0 && heads > 0) {

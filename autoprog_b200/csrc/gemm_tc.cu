@@ -136,20 +136,21 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer (one elected lane) =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int z = item % p.splits, t = item / p.splits;
-        const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
-        const int kb0 = z * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-          uint8_t* sa = smem + s * STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
+    // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
+    const bool leader = elect_one();
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int z = item % p.splits, t = item / p.splits;
+      const int m0 = (t / p.tiles_n) * BM, n0 = (t % p.tiles_n) * BN;
+      const int kb0 = z * p.kb_per_split, kb1 = min(total_kb, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        const int k0 = kb * BK;
+        if (leader) {
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-          const int k0 = kb * BK;
           if (!p.a_mn) {
             tma_load_2d(sa, &tma_a, &full_bar[s], k0, m0);                 // box {64 k, 128 m}
           } else {
@@ -163,20 +164,25 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
             for (int h = 0; h < BN / 64; ++h) tma_load_2d(sb + h * (BK * 128), &tma_b, &full_bar[s], n0 + h * 64, k0);
           }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one elected lane) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
+    {
+      const bool leader = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
-      const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;
+      // k-step of 16 inside a stage, in descriptor units (16 B): K-major +32 B, MN-major +16 rows of 128 B
+      const uint64_t a_kstep = p.a_mn ? (16 * 128) >> 4 : 32 >> 4, b_kstep = p.b_mn ? (16 * 128) >> 4 : 32 >> 4;
       // row sums ride on the tensor pipe: one extra 128 x 16 x 16 MMA per k-step against a tile of ones.  The n-tiles
       // of an m-tile read the same A tiles, so they share the work: n-tile j covers the k-blocks with kb % tiles_n == j
       const uint32_t idesc_rs = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)(RS_COLS >> 3) << 17) |
                                 ((uint32_t)(BM >> 4) << 24);
       const uint64_t ones_desc = make_smem_desc(smem_u32(ones), 16, 1024);
+      const uint32_t smem_a0 = smem_u32(smem);
       uint32_t it = 0, ai = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++ai) {
         const int z = item % p.splits;
@@ -186,33 +192,33 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         const uint32_t as = ai % ACC_STAGES;
         mbar_wait(&tempty_bar[as], ((ai / ACC_STAGES) & 1) ^ 1);      // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem_base + as * BN, trs = tmem_base + ACC_STAGES * BN + as * RS_COLS;
+        const uint32_t tacc = tmem_u + as * BN, trs = tmem_u + ACC_STAGES * BN + as * RS_COLS;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&full_bar[s], (it / STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+          const uint32_t sa = smem_a0 + s * STAGE_BYTES, sb = sa + A_BYTES;
+          const uint64_t ad0 = make_smem_desc(sa, a_lbo, 1024), bd0 = make_smem_desc(sb, b_lbo, 1024);
+          const uint32_t acc_first = kb > kb0 ? 1u : 0u;
           // two straight-line versions of the k-steps (no conditionally executed tensor-core instruction)
-          if (!AUX && p.rowsum != nullptr && (kb % p.tiles_n) == tn) {
+          const bool with_rs = !AUX && p.rowsum != nullptr && (kb % p.tiles_n) == tn;
+          if (leader) {
+            if (with_rs) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
-              const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-              umma_bf16(tacc, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-              umma_bf16(trs, ad, ones_desc, idesc_rs, rs_acc | (uint32_t)(k > 0));
-            }
-            rs_acc = 1u;
-          } else {
+              for (int k = 0; k < BK / 16; ++k) {
+                umma_bf16(tacc, ad0 + k * a_kstep, bd0 + k * b_kstep, idesc, k > 0 ? 1u : acc_first);
+                umma_bf16(trs, ad0 + k * a_kstep, ones_desc, idesc_rs, k > 0 ? 1u : rs_acc);
+              }
+            } else {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
-              const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-              umma_bf16(tacc, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < BK / 16; ++k) umma_bf16(tacc, ad0 + k * a_kstep, bd0 + k * b_kstep, idesc, k > 0 ? 1u : acc_first);
             }
+            umma_commit(&empty_bar[s]);   // frees the smem stage once the MMAs above have read it
+            if (kb + 1 == kb1) umma_commit(&tfull_bar[as]);    // accumulator of this tile complete
           }
-          umma_commit(&empty_bar[s]);   // frees the smem stage once the MMAs above have read it
+          if (with_rs) rs_acc = 1u;
+          __syncwarp();
         }
-        umma_commit(&tfull_bar[as]);    // accumulator of this tile complete
       }
     }
   } else {

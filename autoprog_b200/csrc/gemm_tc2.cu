@@ -119,48 +119,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + EPI_WARPS * 32,
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer (one lane, BOTH CTAs) =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int item = pair; item < n_items; item += npairs) {
-        const int m0 = (item / p.tiles_n) * (2 * BMC) + (int)rank * BMC;
-        const int n0 = (item % p.tiles_n) * BN + (int)rank * (BN / 2);
-        for (int kb = 0; kb < total_kb; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-          uint8_t* sa = smem + s * STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
+    // ===================== TMA producer (BOTH CTAs; whole warp runs the loop, one elected lane issues) =====================
+    const bool leader = elect_one();
+    uint32_t it = 0;
+    for (int item = pair; item < n_items; item += npairs) {
+      const int m0 = (item / p.tiles_n) * (2 * BMC) + (int)rank * BMC;
+      const int n0 = (item % p.tiles_n) * BN + (int)rank * (BN / 2);
+      for (int kb = 0; kb < total_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        const uint32_t lead_full = mapa_rank(smem_u32(&full_bar[s]), 0);
+        if (leader) {
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);      // bytes of both CTAs land on the leader's barrier
-          const uint32_t lead_full = mapa_rank(smem_u32(&full_bar[s]), 0);
           tma_load_2d_pair(sa, &tma_a, lead_full, kb * BK2, m0);            // box {64 k, 128 m}
           tma_load_2d_pair(sb, &tma_b, lead_full, kb * BK2, n0);            // box {64 k, BN/2 n}
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one lane of the LEADER CTA) =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (LEADER CTA; whole warp runs the loop, one elected lane issues) =====================
+    if (rank == 0) {
+      const bool leader = elect_one();
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BMC) >> 4) << 24);
+      const uint32_t smem_a0 = smem_u32(smem);
       uint32_t it = 0, ai = 0;
       for (int item = pair; item < n_items; item += npairs, ++ai) {
         const uint32_t as = ai % ACC2;
         mbar_wait(&tempty_bar[as], ((ai / ACC2) & 1) ^ 1);           // both CTAs' epilogues have drained this stage
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem_base + as * BN;
+        const uint32_t tacc = tmem_u + as * BN;
         for (int kb = 0; kb < total_kb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&full_bar[s], (it / STAGES) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+          const uint32_t sa = smem_a0 + s * STAGE_BYTES, sb = sa + A_BYTES;
+          const uint64_t ad0 = make_smem_desc(sa, 16, 1024), bd0 = make_smem_desc(sb, 16, 1024);
+          const uint32_t acc_first = kb > 0 ? 1u : 0u;
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BK2 / 16; ++k) {
-            const uint64_t ad = make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc(sb + k * 32, 16, 1024);
-            umma_bf16_pair(tacc, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK2 / 16; ++k) umma_bf16_pair(tacc, ad0 + k * 2, bd0 + k * 2, idesc, k > 0 ? 1u : acc_first);
+            umma_commit_pair(&empty_bar[s]);    // frees this smem stage in both CTAs
+            if (kb + 1 == total_kb) umma_commit_pair(&tfull_bar[as]);     // accumulator complete: wakes the epilogues of both CTAs
           }
-          umma_commit_pair(&empty_bar[s]);    // frees this smem stage in both CTAs
+          __syncwarp();
         }
-        umma_commit_pair(&tfull_bar[as]);     // accumulator complete: wakes the epilogues of both CTAs
       }
     }
   } else {

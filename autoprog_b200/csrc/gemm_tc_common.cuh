@@ -10,6 +10,23 @@ namespace {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a CONVERGED warp.  The issuing warps run their loops with all 32 lanes (every loop-carried value
+// stays warp-uniform, so descriptors / coordinates live in uniform registers) and only the tcgen05 / TMA instruction
+// itself sits under this predicate: an `if (lane == 0)` around the whole loop makes every value thread-private and the
+// compiler then wraps EVERY UTCHMMA / UTMALDG in an ELECT + R2UR + BRA.U.ANY waterfall (~90 cycles per instruction,
+// measured with csrc/umma_timing.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

@@ -115,11 +115,12 @@ int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads
                  apb_stream_t stream);
 /* tcgen05 / TMEM / TMA kernels for head_dim 32 and N <= 224 (attention_tc.cu): S (and dP) accumulate in TMEM, one TMEM
  * lane per query row (plain two-pass row softmax, no shuffles), P fed back as the TMEM A operand (forward) or through
- * 64B-swizzled shared tiles read K-major and MN-major (backward: dV, dK, dQ in ONE kernel, row dots computed in-kernel).
+ * 64B-swizzled shared tiles read K-major and MN-major (backward: dV, dK, dQ in ONE kernel after a row-dot pre-pass;
+ * workspace: B*heads*N floats).
  * Return APB_ERR_UNSUPPORTED outside that envelope.  apb_mhsa_fwd / apb_mhsa_bwd use them by default for APB_BF16. */
 int apb_mhsa_fwd_tc(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, apb_stream_t stream);
-int apb_mhsa_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, int B, int N, int heads,
-                    int D, float scale, apb_stream_t stream);
+int apb_mhsa_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* workspace, int B,
+                    int N, int heads, int D, float scale, apb_stream_t stream);
 /* flash-style mma.sync kernels (attention_mma.cu; bf16, head_dim 32 or 64, any N that fits shared memory): scores in
  * registers, online softmax; bwd = row-dot + dQ + dK/dV kernels.  workspace: B*heads*N floats. */
 int apb_mhsa_fwd_mma(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, apb_stream_t stream);
@@ -217,6 +218,12 @@ long long apb_fallback_count(void);
 /* diagnostic (tools/umma_probe.py): D[128,32] = A[128,64] * B[64, off:off+32] through ONE descriptor convention
  * (mode 0..3, see csrc/umma_probe.cu); pins the shared-memory layouts the attention kernels rely on. */
 int apb_debug_umma_probe(const void* A, const void* Bm, float* D, int mode, int off_elems, apb_stream_t stream);
+/* diagnostic (tools/umma_timing.py): SM cycles for `reps` back-to-back tcgen05.mma of one operand-layout kind
+ * (csrc/umma_timing.cu); out4 = {issue cycles, issue + completion cycles} x {warm-up, measured}. */
+int apb_debug_umma_timing(long long* out4, int kind, int N, int reps, apb_stream_t stream);
+/* diagnostic (tools/mhsa_trace.py): device buffer [18][1024] int64; CTA 0 of the following apb_mhsa_*_tc launches logs
+ * (event id << 48 | SM clock) per warp into it.  NULL switches tracing off. */
+int apb_debug_mhsa_trace(long long* buf);
 
 #ifdef __cplusplus
 }

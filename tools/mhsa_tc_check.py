@@ -37,7 +37,8 @@ for (B, N, H) in [(2, 196, 2), (1, 49, 3), (3, 197, 2), (2, 144, 12), (1, 224, 1
     if which in ('all', 'bwd'):
         o_in = o_ref.to(bf)
         dqkv = torch.full_like(qkv, float('nan'))
-        check(lib().apb_mhsa_bwd_tc(qkv.data_ptr(), o_in.data_ptr(), do.data_ptr(), lse_ref.contiguous().data_ptr(), dqkv.data_ptr(), B, N, H, 32, scale, st()), 'bwd_tc')
+        wsb = torch.empty(B * H * N, device=dev)
+        check(lib().apb_mhsa_bwd_tc(qkv.data_ptr(), o_in.data_ptr(), do.data_ptr(), lse_ref.contiguous().data_ptr(), dqkv.data_ptr(), wsb.data_ptr(), B, N, H, 32, scale, st()), 'bwd_tc')
         torch.cuda.synchronize()
         d = dqkv.reshape(B, N, 3, H * 32); r = dqkv_ref.reshape(B, N, 3, H * 32)
         msg += f' bwd dq {rel(d[:, :, 0], r[:, :, 0]):.2e} dk {rel(d[:, :, 1], r[:, :, 1]):.2e} dv {rel(d[:, :, 2], r[:, :, 2]):.2e}'
@@ -63,6 +64,6 @@ for (B, N, H) in [(128, 196, 12), (128, 144, 12), (128, 100, 12), (128, 64, 12)]
         res['fwd_tc'] = t(lambda i: lib().apb_mhsa_fwd_tc(qkvs[i].data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, 32, scale, st()))
     res['fwd_mma'] = t(lambda i: lib().apb_mhsa_fwd_mma(qkvs[i].data_ptr(), out.data_ptr(), lse.data_ptr(), B, N, H, 32, scale, st())) if hasattr(lib(), 'apb_mhsa_fwd_mma') else None
     if which in ('all', 'bwd'):
-        res['bwd_tc'] = t(lambda i: lib().apb_mhsa_bwd_tc(qkvs[i].data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dq.data_ptr(), B, N, H, 32, scale, st()))
+        res['bwd_tc'] = t(lambda i: lib().apb_mhsa_bwd_tc(qkvs[i].data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dq.data_ptr(), ws.data_ptr(), B, N, H, 32, scale, st()))
     res['bwd_mma'] = t(lambda i: lib().apb_mhsa_bwd_mma(qkvs[i].data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dq.data_ptr(), ws.data_ptr(), B, N, H, 32, scale, st())) if hasattr(lib(), 'apb_mhsa_bwd_mma') else None
     print(f'B={B} N={N} heads={H}: ' + '  '.join(f'{k} {v:.1f} us' for k, v in res.items() if v is not None), flush=True)
