@@ -14,6 +14,7 @@ from . import volo, submodels, deit  # noqa: F401  (registers volo_d1..d5, model
 from .volo import VOLO  # noqa: F401
 from .cross_entropy import (SoftTargetCrossEntropy, TokenLabelCrossEntropy, TokenLabelGTCrossEntropy,  # noqa: F401
                             TokenLabelSoftTargetCrossEntropy)
+from .token_label import create_token_label_target  # noqa: F401
 from .progressive import progressive_schedule, make_divisible  # noqa: F401
 from .helpers import new_idx, get_new_layer_idx  # noqa: F401
 from .scaler import NoScaler, Bf16Scaler, NativeScaler, ApexScaler  # noqa: F401

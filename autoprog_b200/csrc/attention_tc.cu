@@ -588,6 +588,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mhsa_bwd_tc_kernel(const __grid_c
           if (!prod_ready[s]) continue;
           const Cur c = mm[s];
           const int gkb = c.ul * nkb + c.kb, j = gkb & 1;            // global key-block counter -> accumulator buffer
+          // FIXED accumulation order (bitwise run-to-run determinism): dK_b / dV_b take the query tiles in order 0, 1 and
+          // dQ takes the key blocks in order 0, 1, ... -- a slot that is early waits for the other one here
+          if (ntq == 2 ? (contrib_of[gkb & 3] != c.qt) : (dq_unit[0] == c.ul ? dq_cnt[0] != c.kb : c.kb != 0)) continue;
           // first contribution to this key block: its accumulator buffer must have been stored (two blocks ago)
           if (contrib_of[gkb & 3] == 0 && gkb >= 2 && !mbar_test_u(&bars->dkv_free[j], ((gkb >> 1) - 1) & 1)) continue;
           // first contribution to dQ of this query tile in this head: the previous head's dQ must have been stored

@@ -392,6 +392,30 @@ class StemConvFn(torch.autograd.Function):
         return None, dw, None, None
 
 
+class ParityConvFn(torch.autograd.Function):
+    """fp32 PARITY mode stem convolution (models/volo.py:355-368; library convolution, TF32 off): the weight gradient is
+    a sum over B*H*W positions of products that almost cancel behind a train-mode BatchNorm (condition number ~1e4 at
+    224 px: torch's own fp32 result is off by 1e-3 against exact arithmetic, cuDNN's serial fp32 accumulation by 2e-3), so
+    parity mode accumulates it in fp64.  Data gradient and forward stay fp32.  Not used by the bf16 training path."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, padding):
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (stride, padding)
+        return torch.nn.functional.conv2d(x, weight, None, stride, padding)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        stride, padding = ctx.cfg
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.nn.grad.conv2d_input(x.shape, weight, dy, stride, padding)
+        if ctx.needs_input_grad[1]:
+            dw = torch.nn.grad.conv2d_weight(x.double(), weight.shape, dy.double(), stride, padding).to(weight.dtype)
+        return dx, dw, None, None
+
+
 class PosEmbedAddFn(torch.autograd.Function):
     """x + bicubic_resize(pos_embed) (models/volo.py:580-596, 627-628); output joins the fp32 residual stream."""
 

@@ -415,6 +415,10 @@ class PatchEmbed(nn.Module):
                     and K.tc_supported(8, m.out_channels, 8)):
                 # few input channels (the 7x7 stem conv on RGB): im2col + tcgen05 GEMM instead of the library conv
                 nhwc = ops.StemConvFn.apply(x, m.weight, m.stride[0], m.padding[0])
+            elif (not torch.is_autocast_enabled('cuda') and x.dtype == torch.float32 and m.bias is None and m.groups == 1
+                  and m.dilation == (1, 1) and isinstance(m.padding[0], int)):
+                # fp32 parity mode: library convolution with the (ill-conditioned) weight gradient accumulated in fp64
+                x = ops.ParityConvFn.apply(x.contiguous(memory_format=torch.channels_last), m.weight, m.stride, m.padding)
             else:
                 x = m(x.contiguous(memory_format=torch.channels_last))
             use_batch = bn.training

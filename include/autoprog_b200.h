@@ -57,6 +57,16 @@ int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, 
  * graph sees a fresh mix-token box on every replay. */
 int apb_scale_by_scalar(const void* in, void* out, long long n, const float* scalar, int dtype, apb_stream_t stream);
 
+/* ---- token-label TARGET builder  (tlt.data.create_token_label_target at main_prog.py:983-1004, 1919-1932; tlt is
+ * un-vendored: recipe restated in oracle/token_label_cpu.py, parity unpinned upstream)
+ * maps fp32 [B,3,5,Hm,Wm]: plane 0 top-5 scores, plane 1 top-5 class ids, plane 2 at [0,0,0:6] = crop box x1,y1,x2,y2
+ * (normalised), flip flag, ground-truth class.  out fp32 [B,C,2+L*L] = what apb_tlce_fwd_bwd takes as its 3-D target:
+ * slot 0 smoothed ground truth, slot 1 class-level label (RoIAlign to 1x1), slots 2.. RoIAlign to LxL; softmax over
+ * classes (apply_softmax), then value*on+off.  apb_onehot_smooth: int64 labels [B] -> smoothed one-hot [B,C]. */
+int apb_token_label_target(const float* maps, float* out, int B, int C, int Hm, int Wm, int label_size, float smoothing,
+                           int apply_softmax, apb_stream_t stream);
+int apb_onehot_smooth(const long long* labels, float* out, int B, int C, float smoothing, apb_stream_t stream);
+
 /* ---- fused residual add (+DropPath per-sample scale) + LayerNorm  (models/volo.py:142-143, 232-233, 306-307)
  * xs = x + rs[row / rows_per_sample] * r (r, rs, xs_out optional);  y = LN(xs) * gamma + beta (y optional).
  * bwd: dxs = dres + LN'(dy) (dres optional); dr = rs[b]*dxs (optional, compute dtype: gradient of the branch r).
