@@ -1,8 +1,7 @@
 // dtype dispatch for ops that have both a tensor-core bf16 kernel and a CUDA-core fp32 kernel.
 #include "common.cuh"
 
-int apb_outlook_fwd_mma(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int lpitch,
-                        cudaStream_t st);
+
 int apb_outlook_bwd_mma(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
                         int heads, float scale, int lpitch, cudaStream_t st);
 
@@ -11,7 +10,15 @@ int apb_outlook_fwd(const void* v, const void* logits, void* y, int B, int H, in
                     int dtype, apb_stream_t stream) {
   if (dtype == APB_BF16 && B > 0 && H > 0 && W > 0 && heads > 0 && lpitch >= heads * 81 && lpitch < heads * 81 + 8 &&
       (((uintptr_t)v | (uintptr_t)y) & 15) == 0) {
-    const int rc = apb_outlook_fwd_mma(v, logits, y, B, H, W, heads, scale, lpitch, APB_STREAM(stream));
+    // two bf16 kernels: the gather formulation on the CUDA cores (outlook_fma.cu) wins on the grids of the early AutoProg
+    // stages (measured at B = 128, 6 heads: 16x16 31 vs 44 us, 20x20 48 vs 73 us, 24x24 90 vs 96 us), the mma.sync
+    // fragments + staged fold (outlook_mma.cu) on 28x28 and wider (128 vs 134 us); each covers the other's unsupported tiles
+    const bool fma_first = W <= 24;
+    int rc = fma_first ? apb_outlook_fwd_fma(v, logits, y, B, H, W, heads, scale, lpitch, stream)
+                       : apb_outlook_fwd_mma(v, logits, y, B, H, W, heads, scale, lpitch, stream);
+    if (rc != APB_ERR_UNSUPPORTED) return rc;
+    rc = fma_first ? apb_outlook_fwd_mma(v, logits, y, B, H, W, heads, scale, lpitch, stream)
+                   : apb_outlook_fwd_fma(v, logits, y, B, H, W, heads, scale, lpitch, stream);
     if (rc != APB_ERR_UNSUPPORTED) return rc;
   }
   if (dtype == APB_BF16) apb_note_fallback("outlook_fwd", "shape / alignment outside the tensor-core kernel's envelope");

@@ -439,7 +439,8 @@ Geo make_geo(int B, int H, int W, int heads, float scale, int lpitch) {
 }  // namespace
 
 int apb_outlook_fwd_mma(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int lpitch,
-                        cudaStream_t st) {
+                        apb_stream_t stream) {
+  cudaStream_t st = APB_STREAM(stream);
   Geo g = make_geo(B, H, W, heads, scale, lpitch);
   size_t smem;
   if (plan(g, false, smem) != 0) return APB_ERR_UNSUPPORTED;

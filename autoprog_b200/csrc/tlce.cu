@@ -29,6 +29,7 @@ struct TlceParams {
   const int* box_dev;          // optional device (bbx1,bby1,bbx2,bby2): overrides lam (CUDA-graph path)
   float w_cls, w_dense;        // already divided by B and B*N
   int tiles_per_img;
+  int cta_offset;              // added to blockIdx.x (the fast path launches only the class-token CTAs of tlce_kernel)
 };
 
 template <typename T>
@@ -39,11 +40,12 @@ __global__ void __launch_bounds__(NTHREADS) tlce_kernel(TlceParams p) {
   __shared__ float s_loss[NTHREADS / 32];
   float my_loss = 0.f;
   const int n_aux_ctas = p.B * p.tiles_per_img;
+  const int bid = (int)blockIdx.x + p.cta_offset;
 
-  if ((int)blockIdx.x < n_aux_ctas) {
+  if (bid < n_aux_ctas) {
     // ---------------- dense part: TT tokens of one image ----------------
-    const int b = blockIdx.x / p.tiles_per_img;
-    const int n0 = (blockIdx.x % p.tiles_per_img) * TT;
+    const int b = bid / p.tiles_per_img;
+    const int n0 = (bid % p.tiles_per_img) * TT;
     const int nt = min(TT, N - n0);
     float* st = reinterpret_cast<float*>(smem_raw);                       // [C][TS]
     T* sx = reinterpret_cast<T*>(smem_raw + (size_t)C * TS * sizeof(float));  // [TT][C]
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(NTHREADS) tlce_kernel(TlceParams p) {
     }
   } else {
     // ---------------- class-token part: one image per warp ----------------
-    const int b0 = ((int)blockIdx.x - n_aux_ctas) * (NTHREADS / 32);
+    const int b0 = (bid - n_aux_ctas) * (NTHREADS / 32);
     const int b = b0 + warp;
     if (b < p.B) {
       const T* xr = reinterpret_cast<const T*>(p.x_cls) + (size_t)b * C;
@@ -126,6 +128,162 @@ __global__ void __launch_bounds__(NTHREADS) tlce_kernel(TlceParams p) {
         float t = t0[(size_t)c * p.t_sc];
         if (mix) t = lam * t + (1.f - lam) * t1[(size_t)c * p.t_sc];
         dr[c] = from_f<T>(p.w_cls * (expf(x - lse) * sum_t - t));
+      }
+    }
+  }
+  if (lane == 0) s_loss[warp] = my_loss;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int i = 0; i < NTHREADS / 32; ++i) s += s_loss[i];
+    p.partial[bid] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fast dense path (3-D class-major target, C a multiple of the 16-byte vector width, C <= 1024: ImageNet's C = 1000).
+// CTA = 16 tokens of one image, 8 warps, 2 tokens per warp:
+//   * each warp first issues the 16-byte loads of ITS two logit rows (4 / 8 vectors per lane, kept in registers), so they
+//     are in flight while
+//   * all warps transpose the [C, 16] target tile into shared memory as token-major fp32 rows: a warp-load covers 4 class
+//     rows x 64 contiguous bytes (8 lanes x float2), and the scalar stores are conflict-free thanks to an XOR swizzle
+//     of the 16-byte chunk index with the token-pair index;
+//   * then a warp owns a token: max, ONE exp per element (kept in the logit registers), sum_t / sum_tx against 16-byte
+//     shared-memory reads of the target row, and the gradient written as 16-byte vectors.
+// One HBM read of each logit and target element, one write of each gradient element; 64 KB of shared memory per CTA.
+constexpr int FT = 16;          // tokens per CTA
+constexpr int FCS = 1024;       // padded row length (floats) of the staged target tile
+
+template <typename T, int MODE> struct FastVec;
+template <int MODE> struct FastVec<bf16, MODE> { static constexpr int V = 8, NJ = 4; };
+template <int MODE> struct FastVec<float, MODE> { static constexpr int V = 4, NJ = 8; };
+
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS, 2) tlce_fast_kernel(TlceParams p) {
+  constexpr int V = FastVec<T, 0>::V, NJ = FastVec<T, 0>::NJ;       // elements per 16-byte vector, vectors per lane per token
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* st = reinterpret_cast<float*>(smem_raw);                  // [FT][FCS], 16-byte chunk index XOR ((token >> 1) & 7)
+  __shared__ float s_loss[NTHREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.C, N = p.N;
+  const int b = blockIdx.x / p.tiles_per_img;
+  const int n0 = (blockIdx.x % p.tiles_per_img) * FT;
+  const int nt = min(FT, N - n0);
+  // ---- (1) this warp's two logit rows -> registers
+  float x[2][NJ * V];
+  bool have[2];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const int n = warp * 2 + q;
+    have[q] = n < nt;
+    const T* xr = reinterpret_cast<const T*>(p.x_aux) + ((size_t)b * N + n0 + n) * C;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = (lane + 32 * j) * V;
+      if (have[q] && c < C) {
+        Vec16<T> v;
+        v.load(xr + c);
+#pragma unroll
+        for (int k = 0; k < V; ++k) x[q][j * V + k] = v.get(k);
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) x[q][j * V + k] = -INFINITY;
+      }
+    }
+  }
+  // ---- (2) target tile [C, FT] -> shared memory [FT][FCS]
+  {
+    const int pq = lane & 7, r = lane >> 3;                          // token pair, class within the warp's group of 4
+    const float* tg = p.target + (size_t)b * p.t_sb + (size_t)(p.slot_aux0 + n0 + 2 * pq);
+    const bool pair_ok = 2 * pq + 1 < nt, first_ok = 2 * pq < nt;
+    const bool vec_ok = (((size_t)b * p.t_sb + (size_t)(p.slot_aux0 + n0)) % 2 == 0) && (p.t_sc % 2 == 0);   // 8-byte aligned float2 loads
+    // UNR independent class rows per lane in flight: all loads first, then the swizzled stores (the loop is otherwise a
+    // chain of dependent load -> store pairs and runs at DRAM latency, not bandwidth)
+    constexpr int UNR = 8;
+    constexpr int CSTEP = (NTHREADS / 32) * 4;
+    for (int cb = warp * 4; cb < C; cb += CSTEP * UNR) {
+      float t0[UNR], t1[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int c = cb + u * CSTEP + r;
+        t0[u] = 0.f; t1[u] = 0.f;
+        if (c < C) {
+          const float* src = tg + (size_t)c * p.t_sc;
+          if (vec_ok && pair_ok) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(src));
+            t0[u] = v.x; t1[u] = v.y;
+          } else {
+            if (first_ok) t0[u] = __ldg(src);
+            if (pair_ok) t1[u] = __ldg(src + 1);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int c = cb + u * CSTEP + r;
+        if (c < C) {
+          const int pc = c ^ (pq << 2);                               // swizzled column
+          st[(2 * pq) * FCS + pc] = t0[u];
+          st[(2 * pq + 1) * FCS + pc] = t1[u];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- (3) one token per warp pass
+  float my_loss = 0.f;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    if (!have[q]) continue;
+    const int n = warp * 2 + q;
+    const float* trow = st + n * FCS;
+    const int key = (n >> 1) & 7;
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < NJ * V; ++i) m = fmaxf(m, x[q][i]);
+    m = warp_max(m);
+    float se = 0.f, sum_t = 0.f, sum_tx = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = (lane + 32 * j) * V;
+      if (c < C) {
+#pragma unroll
+        for (int h = 0; h < V / 4; ++h) {
+          const float4 t4 = *reinterpret_cast<const float4*>(trow + ((((c >> 2) + h) ^ key) << 2));
+          const float tq[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float xv = x[q][j * V + h * 4 + k];
+            sum_t += tq[k];
+            sum_tx = fmaf(tq[k], xv, sum_tx);
+            const float e = __expf(xv - m);
+            x[q][j * V + h * 4 + k] = e;
+            se += e;
+          }
+        }
+      }
+    }
+    se = warp_sum(se);
+    sum_t = warp_sum(sum_t);
+    sum_tx = warp_sum(sum_tx);
+    const float lse = m + logf(se);
+    if (lane == 0) my_loss += p.w_dense * (lse * sum_t - sum_tx);
+    const float a = p.w_dense * sum_t / se;                          // w * sum_t * softmax = a * e
+    T* dr = reinterpret_cast<T*>(p.d_aux) + ((size_t)b * N + n0 + n) * C;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = (lane + 32 * j) * V;
+      if (c < C) {
+        Vec16<T> v;
+#pragma unroll
+        for (int h = 0; h < V / 4; ++h) {
+          const float4 t4 = *reinterpret_cast<const float4*>(trow + ((((c >> 2) + h) ^ key) << 2));     // second shared read, no registers held
+          v.set(h * 4 + 0, fmaf(a, x[q][j * V + h * 4 + 0], -p.w_dense * t4.x));
+          v.set(h * 4 + 1, fmaf(a, x[q][j * V + h * 4 + 1], -p.w_dense * t4.y));
+          v.set(h * 4 + 2, fmaf(a, x[q][j * V + h * 4 + 2], -p.w_dense * t4.z));
+          v.set(h * 4 + 3, fmaf(a, x[q][j * V + h * 4 + 3], -p.w_dense * t4.w));
+        }
+        v.store(dr + c);
       }
     }
   }
@@ -185,9 +343,34 @@ int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, 
   const int n_cls_ctas = (B + NTHREADS / 32 - 1) / (NTHREADS / 32);
   const int grid = B * p.tiles_per_img + n_cls_ctas;
   const size_t esz = dtype == APB_F32 ? 4 : 2;
+  p.cta_offset = 0;
+  cudaError_t e;
+  // fast dense path: class-major 3-D target, 16-byte logit rows, C <= 1024
+  const int vecw = dtype == APB_F32 ? 4 : 8;
+  const bool fast = target_is_3d && C % vecw == 0 && C <= FCS && (((uintptr_t)x_aux | (uintptr_t)d_aux) & 15) == 0;
+  if (fast) {
+    const size_t fsmem = (size_t)FT * FCS * sizeof(float);
+    const int n_aux = B * p.tiles_per_img;
+    if (dtype == APB_F32) {
+      e = cudaFuncSetAttribute(tlce_fast_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+      if (e != cudaSuccess) { apb_set_error("tlce: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+      tlce_fast_kernel<float><<<n_aux, NTHREADS, fsmem, st>>>(p);
+    } else {
+      e = cudaFuncSetAttribute(tlce_fast_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+      if (e != cudaSuccess) { apb_set_error("tlce: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+      tlce_fast_kernel<bf16><<<n_aux, NTHREADS, fsmem, st>>>(p);
+    }
+    APB_LAUNCH_CHECK("tlce_fast_kernel");
+    p.cta_offset = n_aux;                      // class-token CTAs only
+    if (dtype == APB_F32) tlce_kernel<float><<<n_cls_ctas, NTHREADS, 0, st>>>(p);
+    else tlce_kernel<bf16><<<n_cls_ctas, NTHREADS, 0, st>>>(p);
+    APB_LAUNCH_CHECK("tlce_kernel(cls)");
+    tlce_reduce_kernel<<<1, 256, 0, st>>>(workspace, grid, loss);
+    APB_LAUNCH_CHECK("tlce_reduce");
+    return 0;
+  }
   const size_t smem = (size_t)C * TS * sizeof(float) + (size_t)TT * C * esz;
   APB_CHECK_ARG(smem <= 227 * 1024, APB_ERR_UNSUPPORTED, "tlce: C=%d needs %zu B of shared memory (> 227 KB)", C, smem);
-  cudaError_t e;
   if (dtype == APB_F32) {
     e = cudaFuncSetAttribute(tlce_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { apb_set_error("tlce: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
@@ -200,6 +383,36 @@ int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, 
   APB_LAUNCH_CHECK("tlce_kernel");
   tlce_reduce_kernel<<<1, 256, 0, st>>>(workspace, grid, loss);
   APB_LAUNCH_CHECK("tlce_reduce");
+  return 0;
+}
+
+// Lazy in-place scaling for the loss backward: buf *= g / applied, skipped entirely (no memory traffic) when the factor is
+// exactly 1 -- the case of every training step, where the loss is the root of backward.  `applied` (device float, starts
+// at 1) remembers the factor already folded into buf, so repeated backward passes with other upstream gradients stay
+// correct.  Two launches: the scaling kernel only READS applied; a one-thread kernel then records the new value.
+template <typename T>
+__global__ void scale_lazy_kernel(T* __restrict__ buf, size_t n, const float* __restrict__ g, const float* __restrict__ applied) {
+  const float f = *g / *applied;
+  if (f == 1.f) return;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    buf[i] = from_f<T>(to_f(buf[i]) * f);
+}
+__global__ void scale_lazy_commit_kernel(const float* __restrict__ g, float* __restrict__ applied) { *applied = *g; }
+
+int apb_scale_lazy(void* buf_a, long long n_a, void* buf_b, long long n_b, const float* g, float* applied, int dtype,
+                   apb_stream_t stream) {
+  cudaStream_t st = APB_STREAM(stream);
+  for (int i = 0; i < 2; ++i) {
+    void* buf = i ? buf_b : buf_a;
+    const long long n = i ? n_b : n_a;
+    if (buf == nullptr || n <= 0) continue;
+    const int grid = (int)((n + 1023) / 1024 > 148 * 8 ? 148 * 8 : (n + 1023) / 1024);
+    if (dtype == APB_F32) scale_lazy_kernel<float><<<grid, 256, 0, st>>>((float*)buf, (size_t)n, g, applied);
+    else scale_lazy_kernel<bf16><<<grid, 256, 0, st>>>((bf16*)buf, (size_t)n, g, applied);
+    APB_LAUNCH_CHECK("scale_lazy");
+  }
+  scale_lazy_commit_kernel<<<1, 1, 0, st>>>(g, applied);
+  APB_LAUNCH_CHECK("scale_lazy_commit");
   return 0;
 }
 

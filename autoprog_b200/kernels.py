@@ -77,6 +77,12 @@ def tlce_fwd_bwd(x_cls, x_aux, target, box_area: int, w_cls: float, w_dense: flo
     return loss, d_cls, d_aux
 
 
+def scale_lazy(a: torch.Tensor, b: torch.Tensor, g: torch.Tensor, applied: torch.Tensor) -> None:
+    """a, b *= g / applied in place (no memory traffic when the factor is 1); applied <- g.  See apb_scale_lazy."""
+    gs = g.to(torch.float32).reshape(1).contiguous()
+    check(lib().apb_scale_lazy(_p(a), a.numel(), _p(b), b.numel(), _p(gs), _p(applied), dt(a), _st()), 'scale_lazy')
+
+
 def scale_by_scalar(x: torch.Tensor, scalar: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(x)
     s = scalar.to(torch.float32).reshape(1).contiguous()

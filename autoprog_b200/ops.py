@@ -494,13 +494,17 @@ class TokenLabelCEFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_cls, x_aux, target, box_area, w_cls, w_dense, box_dev=None):
         loss, d_cls, d_aux = K.tlce_fwd_bwd(_c(x_cls), _c(x_aux), _c(target), box_area, w_cls, w_dense, box_dev)
-        ctx.save_for_backward(d_cls, d_aux)
+        applied = torch.ones(1, device=loss.device, dtype=F32)     # upstream-gradient factor already folded into d_*
+        ctx.save_for_backward(d_cls, d_aux, applied)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        d_cls, d_aux = ctx.saved_tensors
-        return K.scale_by_scalar(d_cls, g), K.scale_by_scalar(d_aux, g), None, None, None, None, None
+        # the kernel produced the gradients for upstream gradient 1 -- the case of every training step (the loss is the
+        # root of backward): the lazy scale is then a no-op launch instead of a read + write pass over [B, N, C]
+        d_cls, d_aux, applied = ctx.saved_tensors
+        K.scale_lazy(d_cls, d_aux, g, applied)
+        return d_cls, d_aux, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------------------------

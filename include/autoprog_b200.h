@@ -42,6 +42,13 @@ int apb_outlook_fwd(const void* v, const void* logits, void* y, int B, int H, in
                     int dtype, apb_stream_t stream);
 int apb_outlook_bwd(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
                     int heads, float scale, int lpitch, int dtype, apb_stream_t stream);
+/* the two bf16 forward kernels behind apb_outlook_fwd: `_fma` = gather formulation on the CUDA cores (outlook_fma.cu, one
+ * warp per 2x2 output block and head pair), `_mma` = mma.sync fragments + staged fold (outlook_mma.cu); both return
+ * APB_ERR_UNSUPPORTED when their tile does not fit shared memory. */
+int apb_outlook_fwd_fma(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int lpitch,
+                        apb_stream_t stream);
+int apb_outlook_fwd_mma(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int lpitch,
+                        apb_stream_t stream);
 /* lpitch: elements between consecutive windows in logits/dlogits, heads*81 <= lpitch < heads*81+8.  The bf16 path
  * pads 486 -> 488 so the producing / consuming GEMMs satisfy TMA's 16-byte row pitch; backward zero-fills the pad. */
 
@@ -56,6 +63,11 @@ int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, 
 /* box_dev: optional DEVICE int[4] (bbx1,bby1,bbx2,bby2) read by the kernel instead of box_area, so a captured CUDA
  * graph sees a fresh mix-token box on every replay. */
 int apb_scale_by_scalar(const void* in, void* out, long long n, const float* scalar, int dtype, apb_stream_t stream);
+/* backward of the fused loss: the gradients above were produced for upstream gradient 1; this folds the real upstream
+ * gradient g (DEVICE scalar) into both buffers IN PLACE and returns without touching memory when g / applied == 1 (every
+ * training step).  applied: device float, initialised to 1 by the caller, remembers the factor already folded in. */
+int apb_scale_lazy(void* buf_a, long long n_a, void* buf_b, long long n_b, const float* g, float* applied, int dtype,
+                   apb_stream_t stream);
 
 /* ---- token-label TARGET builder  (tlt.data.create_token_label_target at main_prog.py:983-1004, 1919-1932; tlt is
  * un-vendored: recipe restated in oracle/token_label_cpu.py, parity unpinned upstream)
