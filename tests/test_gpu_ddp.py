@@ -1,9 +1,11 @@
 """Data-parallel path on real GPUs (NCCL, world_size 2; skipped on a single-GPU box):
   * eager hooks: reduced gradients == mean of the per-rank local gradients, for EVERY parameter -- including the ones
     whose gradient autograd allocates itself (cuDNN stem convolutions) rather than a kernel writing the flat buffer;
-  * replicas stay bit-identical over several optimizer steps, eager and CUDA-graph mode (two graphs around the eager
-    all-reduce), although every rank sees different data.
-Reference behaviour: torch DistributedDataParallel as used by train.py:385-397 (averaged gradients, identical replicas).
+  * replicas stay bit-identical over several optimizer steps although every rank sees different data: eager, CUDA-graph
+    mode with the bucketed all-reduces captured INSIDE the graph and overlapped with backward ('overlap'), and the
+    two-graph fallback around an eager all-reduce ('split').
+Reference behaviour: apex / torch DistributedDataParallel as wrapped at main_prog.py:538-549 (averaged gradients,
+identical replicas).
 """
 import os
 import socket
@@ -30,7 +32,7 @@ def _worker(rank, world, port, out):
     from autoprog_b200.graph import GraphedTrainStep
     from autoprog_b200.optim import FusedAdamW
     res = {}
-    for mode in ('eager', 'graph'):
+    for mode in ('eager', 'overlap', 'split'):
         torch.manual_seed(100 + rank)                # different init per rank: the wrapper broadcasts rank 0's
         m = A.create_model('model_variant', variant='volo_h2_l4', img_size=64, num_classes=16).to(dev)
         opt = FusedAdamW(m, lr=1e-3, weight_decay=0.05)
@@ -67,7 +69,7 @@ def _worker(rank, world, port, out):
                 opt.step()
         else:
             np.random.seed(5)
-            step = GraphedTrainStep(net, crit, opt, x, tgt, bf16=True, warmup=3)
+            step = GraphedTrainStep(net, crit, opt, x, tgt, bf16=True, warmup=3, ddp_mode=mode)
             for _ in range(3):
                 step()
             step.close()
@@ -88,6 +90,8 @@ def test_ddp_two_gpus_nccl(tmp_path):
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     r0, r1 = torch.load(out + '.0'), torch.load(out + '.1')
     assert r0['grad_vs_mean'] < 1e-5 and r1['grad_vs_mean'] < 1e-5, (r0['grad_vs_mean'], r1['grad_vs_mean'])
-    for mode in ('eager', 'graph'):
+    for mode in ('eager', 'overlap', 'split'):
         assert torch.isfinite(r0[mode]).all()
         assert torch.equal(r0[mode], r1[mode]), mode       # replicas identical after 3 steps on different data
+    # the graph modes run the same 3 steps as each other (warm-up is rolled back): identical weights
+    assert torch.equal(r0['overlap'], r0['split'])
