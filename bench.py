@@ -763,13 +763,17 @@ def measure_rooflines(train_step, x, t, K, torch, B, bf16):
     setattr(K, 'mhsa_fwd', wrap('mhsa_fwd', mhsa_work))
     setattr(K, 'mhsa_bwd', wrap('mhsa_bwd', lambda qkv, *a, **kw: 2.5 * mhsa_work(qkv)))     # 5 products vs 2
     try:
-        for _ in range(2):            # first pass warms the caching allocator
+        host_s = 0.05
+        for it in range(3):           # first pass warms the caching allocator, second one times the host's enqueue
             for v in rec.values():
                 v.clear()
-            # park the GPU while the host enqueues the step: every event pair then brackets back-to-back device work
-            # only (an eager host that falls behind would otherwise leave idle time inside the spans)
-            torch.cuda._sleep(int(80e6))
+            # park the GPU for as long as the host needs to enqueue the WHOLE step (measured in the previous pass, +50 %):
+            # every event pair then brackets back-to-back device work only (an eager host that falls behind would
+            # otherwise leave idle time inside the spans)
+            torch.cuda._sleep(int(min(host_s * 1.5, 1.0) * 2.0e9))
+            h0 = time.perf_counter()
             train_step(x, t)
+            host_s = time.perf_counter() - h0
             torch.cuda.synchronize()
     finally:
         for n in names:
