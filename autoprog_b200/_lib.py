@@ -74,6 +74,8 @@ SIGNATURES = {
     'apb_adamw_ema': (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, C.POINTER(_vp), C.POINTER(_f), _i, _vp, _vp]),
     'apb_launch_count': (_ll, []),
     'apb_fallback_count': (_ll, []),
+    'apb_set_pdl': (None, [_i]),
+    'apb_get_pdl': (_i, []),
     'apb_debug_umma_probe': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     'apb_debug_umma_timing': (_i, [_vp, _i, _i, _i, _vp]),
     'apb_debug_mhsa_trace': (_i, [_vp]),

@@ -37,6 +37,30 @@ extern long long g_apb_launches;   // kernel launches issued through the library
 
 typedef __nv_bfloat16 bf16;
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// A kernel launched through apb_launch_pdl may begin (block scheduling, barrier / TMEM setup, tensor-map prefetch) while
+// its predecessor in the stream is still draining; it must execute pdl_wait() BEFORE its first global-memory access (the
+// wait returns once every prerequisite grid has completed and its writes are visible).  pdl_trigger() lets the NEXT
+// kernel in the stream start its own prologue; it is placed after the wait, so at most two grids are in flight.
+// Both instructions are no-ops for a kernel launched without the attribute.  g_apb_pdl: APB_PDL=0 disables the attribute.
+extern int g_apb_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t apb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_apb_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
 template <typename T> __device__ __forceinline__ T from_f(float x);

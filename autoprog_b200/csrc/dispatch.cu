@@ -10,15 +10,12 @@ int apb_outlook_fwd(const void* v, const void* logits, void* y, int B, int H, in
                     int dtype, apb_stream_t stream) {
   if (dtype == APB_BF16 && B > 0 && H > 0 && W > 0 && heads > 0 && lpitch >= heads * 81 && lpitch < heads * 81 + 8 &&
       (((uintptr_t)v | (uintptr_t)y) & 15) == 0) {
-    // two bf16 kernels: the gather formulation on the CUDA cores (outlook_fma.cu) wins on the grids of the early AutoProg
-    // stages (measured at B = 128, 6 heads: 16x16 31 vs 44 us, 20x20 48 vs 73 us, 24x24 90 vs 96 us), the mma.sync
-    // fragments + staged fold (outlook_mma.cu) on 28x28 and wider (128 vs 134 us); each covers the other's unsupported tiles
-    const bool fma_first = W <= 24;
-    int rc = fma_first ? apb_outlook_fwd_fma(v, logits, y, B, H, W, heads, scale, lpitch, stream)
-                       : apb_outlook_fwd_mma(v, logits, y, B, H, W, heads, scale, lpitch, stream);
+    // two bf16 kernels: the gather formulation on the CUDA cores (outlook_fma.cu) is the faster one on every AutoProg grid
+    // (measured at B = 128, 6 heads: 16x16 29 vs 44 us, 20x20 42 vs 73, 24x24 59 vs 96, 28x28 78 vs 128); the mma.sync
+    // fragments + staged fold (outlook_mma.cu) cover the tiles it declines (unaligned logits rows, oversized bands)
+    int rc = apb_outlook_fwd_fma(v, logits, y, B, H, W, heads, scale, lpitch, stream);
     if (rc != APB_ERR_UNSUPPORTED) return rc;
-    rc = fma_first ? apb_outlook_fwd_mma(v, logits, y, B, H, W, heads, scale, lpitch, stream)
-                   : apb_outlook_fwd_fma(v, logits, y, B, H, W, heads, scale, lpitch, stream);
+    rc = apb_outlook_fwd_mma(v, logits, y, B, H, W, heads, scale, lpitch, stream);
     if (rc != APB_ERR_UNSUPPORTED) return rc;
   }
   if (dtype == APB_BF16) apb_note_fallback("outlook_fwd", "shape / alignment outside the tensor-core kernel's envelope");

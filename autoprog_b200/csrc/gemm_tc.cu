@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
@@ -166,6 +167,9 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         }
         __syncwarp();
       }
+      // last tile's loads are in flight: let the next kernel in the stream get scheduled and run its prologue while this
+      // CTA finishes (not earlier: a dependent CTA parked on this SM for the whole kernel competes for issue slots)
+      if (item + (int)gridDim.x >= n_items) pdl_trigger();
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
@@ -394,7 +398,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
   p.splits = splits;
   const long long items = (long long)p.tiles_m * p.tiles_n * splits;
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  gemm_tc_kernel<BN, STAGES, EPI_WARPS, AUX><<<grid, 64 + EPI_WARPS * 32, smem, st>>>(ma, mb, mc, mx, p);
+  apb_launch_pdl(gemm_tc_kernel<BN, STAGES, EPI_WARPS, AUX>, dim3(grid), dim3(64 + EPI_WARPS * 32), smem, st, ma, mb, mc, mx, p);
   APB_LAUNCH_CHECK("gemm_tc");
   return 0;
 }

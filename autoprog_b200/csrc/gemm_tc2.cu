@@ -117,6 +117,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + EPI_WARPS * 32,
   cluster_sync_all();                                   // barriers of both CTAs initialised before any remote signal
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();        // the prologue above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer (BOTH CTAs; whole warp runs the loop, one elected lane issues) =====================
@@ -138,6 +139,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + EPI_WARPS * 32,
         }
         __syncwarp();
       }
+      if (item + npairs >= n_items) pdl_trigger();     // last tile's loads in flight: the next kernel may start its prologue
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (LEADER CTA; whole warp runs the loop, one elected lane issues) =====================
@@ -263,7 +265,7 @@ int launch2(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc,
   const long long items = (long long)p.tiles_m * p.tiles_n;
   const int pairs_max = num_sms() / 2;
   const int pairs = (int)(items < pairs_max ? items : pairs_max);
-  gemm_tc2_kernel<BN, STAGES, EPI_WARPS><<<2 * pairs, 64 + EPI_WARPS * 32, smem, st>>>(ma, mb, mc, p);
+  apb_launch_pdl(gemm_tc2_kernel<BN, STAGES, EPI_WARPS>, dim3(2 * pairs), dim3(64 + EPI_WARPS * 32), smem, st, ma, mb, mc, p);
   APB_LAUNCH_CHECK("gemm_tc2");
   return 0;
 }

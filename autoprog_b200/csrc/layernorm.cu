@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(1024) colsum_partials_kernel(const float* __re
                                                                const float* __restrict__ part1, float* __restrict__ out1,
                                                                int nparts, int C, int accumulate) {
   __shared__ float s[32][33];
+  pdl_wait();
+  pdl_trigger();
   const float* part = blockIdx.y == 0 ? part0 : part1;
   float* out = blockIdx.y == 0 ? out0 : out1;
   const int lane = threadIdx.x & 31, ph = threadIdx.x >> 5;
@@ -251,7 +253,7 @@ int apb_ln_bwd(const void* dy, const void* xs, const float* mean, const float* r
                                          sdtype, cdtype, st);
     if (handled == 1) {
       APB_LAUNCH_CHECK("ln_bwd_v4");
-      colsum_partials_kernel<<<dim3(ceil_div(C, 32), 2), 1024, 0, st>>>(pg, dgamma, pb, dbeta, grid, C, accumulate);
+      apb_launch_pdl(colsum_partials_kernel, dim3(ceil_div(C, 32), 2), dim3(1024), 0, st, pg, dgamma, pb, dbeta, grid, C, accumulate);
       APB_LAUNCH_CHECK("ln_bwd_reduce");
       return 0;
     }
@@ -281,7 +283,7 @@ int apb_ln_bwd(const void* dy, const void* xs, const float* mean, const float* r
 #undef LN_BWD
 #undef LN_BWD_NV
   APB_LAUNCH_CHECK("ln_bwd");
-  colsum_partials_kernel<<<dim3(ceil_div(C, 32), 2), 1024, 0, st>>>(pg, dgamma, pb, dbeta, grid, C, accumulate);
+  apb_launch_pdl(colsum_partials_kernel, dim3(ceil_div(C, 32), 2), dim3(1024), 0, st, pg, dgamma, pb, dbeta, grid, C, accumulate);
   APB_LAUNCH_CHECK("ln_bwd_reduce");
   return 0;
 }
@@ -311,7 +313,7 @@ int apb_colsum(const void* a, long long rows, int C, float* out, int accumulate,
     else colsum_stage1_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)a, rows, C, workspace, rows_per_cta);
   }
   APB_LAUNCH_CHECK("colsum_stage1");
-  colsum_partials_kernel<<<dim3(ceil_div(C, 32), 1), 1024, 0, st>>>(workspace, out, nullptr, nullptr, parts, C, accumulate);
+  apb_launch_pdl(colsum_partials_kernel, dim3(ceil_div(C, 32), 1), dim3(1024), 0, st, workspace, out, nullptr, nullptr, parts, C, accumulate);
   APB_LAUNCH_CHECK("colsum_stage2");
   return 0;
 }

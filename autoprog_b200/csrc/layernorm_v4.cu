@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(256) ln_bwd_v4_kernel(const TC* __restrict__ d
                                                         float* __restrict__ part_g, float* __restrict__ part_b,
                                                         long long rows, int C) {
   extern __shared__ float sm[];  // [nwarp][2][C]
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int ngroups = C >> 2;
   int off[NG];
@@ -112,6 +114,8 @@ __global__ void __launch_bounds__(256) ln_fwd_v4_kernel(const TS* __restrict__ x
                                                         TS* __restrict__ xs_out, TC* __restrict__ y,
                                                         float* __restrict__ mean, float* __restrict__ rstd, long long rows,
                                                         int C, float eps) {
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -183,6 +187,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) colsum_v8_kernel(const T* __restrict__ a, long long rows, int C,
                                                         float* __restrict__ part, int rows_per_cta, int TX) {
   __shared__ __align__(16) float s[256 * 8];              // [TY][TX * 8]
+  pdl_wait();
+  pdl_trigger();
   const int TY = 256 / TX;
   const int ty = threadIdx.x / TX, tx = threadIdx.x - ty * TX;
   const int c0 = (blockIdx.x * TX + tx) * 8;
@@ -237,6 +243,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
                                                             long long n4, const float* __restrict__ parts2,
                                                             float* __restrict__ out2, long long n4b, int splits2) {
   __shared__ float4 sm[4][64];
+  pdl_wait();
+  pdl_trigger();
   const int tx = threadIdx.x & 63, g = threadIdx.x >> 6;
   const long long i = (long long)blockIdx.x * 64 + tx;
   const bool live = i < n4 + n4b;
@@ -281,7 +289,8 @@ int apb_splitk_reduce2(const float* parts, float* out, long long n, int splits, 
   const long long n4 = n / 4, n4b = n2 / 4;
   const long long grid = (n4 + n4b + 63) / 64;
   APB_CHECK_ARG(grid <= 0x7fffffffLL, APB_ERR_SHAPE, "splitk_reduce: n too large");
-  splitk_reduce_kernel<<<(int)grid, 256, 0, st>>>(parts, out, splits, n4, parts2, out2, n4b, splits2 < 1 ? 1 : splits2);
+  apb_launch_pdl(splitk_reduce_kernel, dim3((unsigned)grid), dim3(256), 0, st, parts, out, splits, n4, parts2, out2, n4b,
+                 splits2 < 1 ? 1 : splits2);
   APB_LAUNCH_CHECK("splitk_reduce");
   return 0;
 }
@@ -302,9 +311,8 @@ int ln_bwd_v4_launch(const void* dy, const void* xs, const float* mean, const fl
 #define V4(NG_, TS_, TC_)                                                                                             \
   do {                                                                                                                \
     cudaFuncSetAttribute(ln_bwd_v4_kernel<NG_, TS_, TC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    ln_bwd_v4_kernel<NG_, TS_, TC_><<<grid, 256, smem, st>>>((const TC_*)dy, (const TS_*)xs, mean, rstd, gamma,        \
-                                                             (const TS_*)dres, (TS_*)dxs, (TC_*)dr, rs, rows_per_sample, \
-                                                             pg, pb, rows, C);                                        \
+    apb_launch_pdl(ln_bwd_v4_kernel<NG_, TS_, TC_>, dim3(grid), dim3(256), smem, st, (const TC_*)dy, (const TS_*)xs, mean, rstd, \
+                   gamma, (const TS_*)dres, (TS_*)dxs, (TC_*)dr, rs, rows_per_sample, pg, pb, rows, C);               \
   } while (0)
 #define V4_T(TS_, TC_)                  \
   do {                                  \
@@ -333,8 +341,8 @@ int ln_fwd_v4_launch(const void* x, const void* r, const float* rs, int rows_per
   const int ng = (C / 4 + 31) / 32;
   const int grid = ceil_div(rows, 8);
 #define F4(NG_, TS_, TC_)                                                                                            \
-  ln_fwd_v4_kernel<NG_, TS_, TC_><<<grid, 256, 0, st>>>((const TS_*)x, (const TC_*)r, rs, rows_per_sample, gamma, beta, \
-                                                        (TS_*)xs_out, (TC_*)y, mean, rstd, rows, C, eps)
+  apb_launch_pdl(ln_fwd_v4_kernel<NG_, TS_, TC_>, dim3(grid), dim3(256), 0, st, (const TS_*)x, (const TC_*)r, rs,        \
+                 rows_per_sample, gamma, beta, (TS_*)xs_out, (TC_*)y, mean, rstd, rows, C, eps)
 #define F4_T(TS_, TC_)                  \
   do {                                  \
     if (ng <= 1) F4(1, TS_, TC_);       \
@@ -371,8 +379,8 @@ int colsum_v8_launch(const void* a, long long rows, int C, float* part, int dtyp
   int gx, TX, rpc, parts;
   colsum_plan(rows, C, &gx, &TX, &rpc, &parts);
   dim3 grid(gx, parts);
-  if (dtype == APB_F32) colsum_v8_kernel<float><<<grid, 256, 0, st>>>((const float*)a, rows, C, part, rpc, TX);
-  else if (dtype == APB_BF16) colsum_v8_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)a, rows, C, part, rpc, TX);
+  if (dtype == APB_F32) apb_launch_pdl(colsum_v8_kernel<float>, grid, dim3(256), 0, st, (const float*)a, rows, C, part, rpc, TX);
+  else if (dtype == APB_BF16) apb_launch_pdl(colsum_v8_kernel<bf16>, grid, dim3(256), 0, st, (const bf16*)a, rows, C, part, rpc, TX);
   else return 0;
   return 1;
 }

@@ -8,9 +8,12 @@
 //   Y[y, x, head, :] = sum over the 1 / 2 / 4 windows (i, j) covering (y, x), with P = position of (y, x) in the window,
 //                      sum_Q softmax_Q(scale * logits[i, j, head, P, :])[Q] * V[pixel Q of window (i, j), head, :]
 // CTA = two output rows (2r, 2r+1) x a range of columns x all heads.
-//   stage 1: the 5-row pixel band of v (zero border) -> shared memory with 16-byte loads; the logits rows the tile needs
-//            (window row r: P rows 3..8; window row r+1: P rows 0..2) -> shared memory as fp32, coalesced reads
-//   stage 2: one thread per (window, head, P) row: softmax over its 9 logits in place (fp32, row pitch 12 floats)
+//   stage 1: the 5-row pixel band of v (zero border) and the raw logits rows of the tile's windows (window rows r and r+1,
+//            whole 16-byte vectors of the padded row) -> shared memory with cp.async (zero-fill outside the image): every
+//            load of the CTA is in flight at once and no register is staged (the register-staged version spent 40 % of its
+//            time on long-scoreboard stalls, profiles/r2_kernels.md)
+//   stage 2: one thread per (window, head, P) row: its 9 logits (window row r: P rows 3..8; window row r+1: P rows 0..2)
+//            from the raw rows -> softmax in fp32 -> weight row (pitch 12 floats)
 //   stage 3: one warp per (2 x 2 output block, head pair): lane = (head of the pair, channel pair); the block's 5 x 5 pixel
 //            patch of v is loaded ONCE into registers (25 x 32-bit shared loads per lane), the 9 weight rows that feed the
 //            four output pixels arrive as broadcast 16-byte loads, 162 FFMA per lane, four 4-byte stores per lane
@@ -36,6 +39,10 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {     // src_bytes 0 -> 16 zero bytes
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
 struct OfParams {
   const bf16* v;
   const bf16* logits;
@@ -57,86 +64,79 @@ __global__ void __launch_bounds__(FMA_THREADS) outlook_fwd_fma_kernel(OfParams p
   const int nblk = min(p.tcw, p.w - jb);                 // output blocks in this tile
   const int nwin = nblk + 1;                             // window columns jb .. jb + nblk (the last one feeds only odd x)
   const int BW = 2 * nblk + 3;                           // band pixel columns: 2 jb - 1 .. 2 (jb + nblk) + 1
-  // shared memory: band [5][BW][C] bf16 | weights [nwin][heads][9][WP] fp32
+  // shared memory: band [5][BW][C] bf16 | weights [nwin][heads][9][WP] fp32 | raw logits [2][nwin][lpitch] bf16
   bf16* band = reinterpret_cast<bf16*>(smem_raw);
   const size_t band_bytes = ((size_t)5 * BW * C * sizeof(bf16) + 15) & ~(size_t)15;
   float* wts = reinterpret_cast<float*>(smem_raw + band_bytes);
+  const size_t wts_bytes = (size_t)nwin * p.heads * 9 * WP * sizeof(float);
+  bf16* raw = reinterpret_cast<bf16*>(smem_raw + band_bytes + wts_bytes);
 
-  // ---- stage 1a: pixel band (rows 2r-1 .. 2r+3, columns 2jb-1 .. ), zeros outside the image.  No divisions in the loops:
-  //      a thread walks (band column, 16-byte vector) with a precomputed stride; all five rows of a position are loaded
-  //      before they are stored (five independent 16-byte loads in flight per thread)
+  // ---- stage 1a: pixel band (rows 2r-1 .. 2r+3, columns 2jb-1 .. ), zeros outside the image.  No divisions in the loop:
+  //      a thread walks (band column, 16-byte vector) with a precomputed stride
   {
     const int vpp = C / 8;                                // 16-byte vectors per pixel
     const int step_bc = FMA_THREADS / vpp, step_cv = FMA_THREADS % vpp;
     int bc = tid / vpp, cv = tid % vpp;
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    uint4* band4 = reinterpret_cast<uint4*>(band);
+    const uint32_t band_s = smem_u32f(band);
     while (bc < BW) {
       const int xx = 2 * jb - 1 + bc;
       const bool xin = xx >= 0 && xx < p.W;
-      uint4 val[5];
 #pragma unroll
       for (int br = 0; br < 5; ++br) {
         const int yy = 2 * r - 1 + br;
-        val[br] = z;
-        if (xin && yy >= 0 && yy < p.H) val[br] = __ldg(reinterpret_cast<const uint4*>(p.v + (((size_t)b * p.H + yy) * p.W + xx) * C) + cv);
+        const bool ok = xin && yy >= 0 && yy < p.H;
+        const bf16* src = ok ? p.v + (((size_t)b * p.H + yy) * p.W + xx) * C + cv * 8 : p.v;
+        cp_async16(band_s + (uint32_t)(((br * BW + bc) * vpp + cv) * 16), src, ok ? 16 : 0);
       }
-#pragma unroll
-      for (int br = 0; br < 5; ++br) band4[(br * BW + bc) * vpp + cv] = val[br];
       bc += step_bc;
       cv += step_cv;
       if (cv >= vpp) { cv -= vpp; ++bc; }
     }
   }
-  // ---- stage 1b: raw logits -> fp32.  Per (window column, head): slot 0 = window row r, elements 27..80 (P = 3..8) ->
-  //      weight rows 0..5; slot 1 = window row r+1, elements 0..26 (P = 0..2) -> weight rows 6..8.  One warp per (window
-  //      column, head): lane l takes elements l, l+32, l+64 of the 81 (constant divisors, three independent loads)
+  // ---- stage 1b: raw logits rows of windows (r, jb ..) and (r+1, jb ..): lpitch * 2 / 16 vectors per window
   {
-    const int nwh = nwin * p.heads;
-    int hd = warp % p.heads, jl = warp / p.heads;
-    const int dh = (FMA_THREADS / 32) % p.heads, dj = (FMA_THREADS / 32) / p.heads;
-    for (int wh = warp; wh < nwh; wh += FMA_THREADS / 32) {
-      const int jw = jb + jl;
-      float val[3];
-#pragma unroll
-      for (int t3 = 0; t3 < 3; ++t3) {
-        const int k = lane + 32 * t3;
-        val[t3] = 0.f;
-        if (k < 81) {
-          const int slot = k >= 54 ? 1 : 0;
-          const int el = slot ? k - 54 : k + 27;          // element inside the head's 81 logits
-          const int iw = r + slot;
-          if (iw < p.h && jw < p.w)
-            val[t3] = __bfloat162float(p.logits[(((size_t)b * p.h + iw) * p.w + jw) * p.lpitch + hd * 81 + el]) * p.scale;
-        }
-      }
-#pragma unroll
-      for (int t3 = 0; t3 < 3; ++t3) {
-        const int k = lane + 32 * t3;
-        if (k < 81) wts[((size_t)wh * 9 + k / 9) * WP + k % 9] = val[t3];     // k / 9 = weight row: 0..5 (slot 0), 6..8 (slot 1)
-      }
-      hd += dh; jl += dj;
-      if (hd >= p.heads) { hd -= p.heads; ++jl; }
+    const int vpw = p.lpitch / 8;
+    const int step_w = FMA_THREADS / vpw, step_v = FMA_THREADS % vpw;
+    int wi = tid / vpw, vv = tid % vpw;                   // wi = slot * nwin + jl
+    const uint32_t raw_s = smem_u32f(raw);
+    while (wi < 2 * nwin) {
+      const int slot = wi >= nwin ? 1 : 0, jl = wi - slot * nwin;
+      const int iw = r + slot, jw = jb + jl;
+      const bool ok = iw < p.h && jw < p.w;
+      const bf16* src = ok ? p.logits + (((size_t)b * p.h + iw) * p.w + jw) * p.lpitch + vv * 8 : p.logits;
+      cp_async16(raw_s + (uint32_t)((wi * vpw + vv) * 16), src, ok ? 16 : 0);
+      wi += step_w;
+      vv += step_v;
+      if (vv >= vpw) { vv -= vpw; ++wi; }
     }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  // ---- stage 2: row softmax in place (rows of windows outside the grid become zeros); thread = (window-head, row)
+  // ---- stage 2: thread = (window-head, weight row): 9 raw logits -> softmax -> fp32 weight row (rows of windows outside the
+  //      grid become zeros).  Weight rows 0..5 = window row r, P = 3..8; rows 6..8 = window row r+1, P = 0..2
   {
     const int nwh = nwin * p.heads;
     for (int e = tid; e < nwh * 9; e += FMA_THREADS) {
       const int ridx = e % 9, wh = e / 9;
-      const int jl = wh / p.heads;
-      const int iw = r + (ridx >= 6 ? 1 : 0), jw = jb + jl;
+      const int jl = wh / p.heads, hd = wh - jl * p.heads;
+      const int slot = ridx >= 6 ? 1 : 0, P = slot ? ridx - 6 : ridx + 3;
+      const int iw = r + slot, jw = jb + jl;
       float* row = wts + (size_t)e * WP;
-      float4 a = *reinterpret_cast<float4*>(row), c4 = *reinterpret_cast<float4*>(row + 4);
-      float l8 = row[8];
+      float4 a, c4;
+      float l8;
       if (iw < p.h && jw < p.w) {
-        float m = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(c4.x, c4.y), fmaxf(fmaxf(c4.z, c4.w), l8)));
-        a.x = __expf(a.x - m); a.y = __expf(a.y - m); a.z = __expf(a.z - m); a.w = __expf(a.w - m);
-        c4.x = __expf(c4.x - m); c4.y = __expf(c4.y - m); c4.z = __expf(c4.z - m); c4.w = __expf(c4.w - m);
-        l8 = __expf(l8 - m);
-        const float inv = 1.f / (((a.x + a.y) + (a.z + a.w)) + ((c4.x + c4.y) + (c4.z + c4.w)) + l8);
-        a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv; c4.x *= inv; c4.y *= inv; c4.z *= inv; c4.w *= inv; l8 *= inv;
+        const bf16* src = raw + (size_t)(slot * nwin + jl) * p.lpitch + hd * 81 + P * 9;
+        float q[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) q[i] = __bfloat162float(src[i]) * p.scale;
+        const float m = fmaxf(fmaxf(fmaxf(q[0], q[1]), fmaxf(q[2], q[3])), fmaxf(fmaxf(q[4], q[5]), fmaxf(fmaxf(q[6], q[7]), q[8])));
+#pragma unroll
+        for (int i = 0; i < 9; ++i) q[i] = __expf(q[i] - m);
+        const float inv = 1.f / (((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7])) + q[8]);
+        a = make_float4(q[0] * inv, q[1] * inv, q[2] * inv, q[3] * inv);
+        c4 = make_float4(q[4] * inv, q[5] * inv, q[6] * inv, q[7] * inv);
+        l8 = q[8] * inv;
       } else {
         a = make_float4(0.f, 0.f, 0.f, 0.f); c4 = a; l8 = 0.f;
       }
@@ -229,18 +229,21 @@ int apb_outlook_fwd_fma(const void* v, const void* logits, void* y, int B, int H
   p.v = (const bf16*)v; p.logits = (const bf16*)logits; p.y = (bf16*)y;
   p.B = B; p.H = H; p.W = W; p.h = (H + 1) / 2; p.w = (W + 1) / 2; p.heads = heads; p.lpitch = lpitch; p.scale = scale;
   const int C = heads * HD;
+  if (lpitch % 8 != 0 || lpitch < heads * 81 || ((uintptr_t)logits & 15) != 0) return APB_ERR_UNSUPPORTED;   // raw rows are staged as 16-byte vectors
   auto smem_for = [&](int tcw) {
     const size_t band = ((size_t)5 * (2 * tcw + 3) * C * 2 + 15) & ~(size_t)15;
-    return band + (size_t)(tcw + 1) * heads * 9 * WP * 4;
+    return band + (size_t)(tcw + 1) * heads * 9 * WP * 4 + (size_t)2 * (tcw + 1) * lpitch * 2;
   };
-  // widest tile that leaves room for two CTAs per SM; else the widest that fits at all
+  // widest tile that leaves room for three CTAs per SM (18 warps); else two; else the widest that fits at all
   int tcw = p.w;
-  while (tcw > 1 && smem_for(tcw) > 113 * 1024) --tcw;
-  if (smem_for(tcw) > 113 * 1024) {
+  const size_t budgets[3] = {75 * 1024, 113 * 1024, 227 * 1024};
+  int bi = 0;
+  for (; bi < 3; ++bi) {
     tcw = p.w;
-    while (tcw > 1 && smem_for(tcw) > 227 * 1024) --tcw;
-    if (smem_for(tcw) > 227 * 1024) return APB_ERR_UNSUPPORTED;
+    while (tcw > 1 && smem_for(tcw) > budgets[bi]) --tcw;
+    if (smem_for(tcw) <= budgets[bi] && (tcw >= 4 || tcw == p.w || bi == 2)) break;
   }
+  if (bi == 3 || smem_for(tcw) > 227 * 1024) return APB_ERR_UNSUPPORTED;
   // balance the column tiles
   p.xtiles = ceil_div(p.w, tcw);
   p.tcw = ceil_div(p.w, p.xtiles);

@@ -8,9 +8,10 @@
 //   sampling, aligned = false) [+ horizontal flip]  ->  softmax over classes  ->  * on + off;   slot 1 = the same with a
 //   1 x 1 output, slot 0 = smoothed one-hot of the ground-truth class.
 // The dense [B, C, Hm, Wm] map (C = 1000) is never materialised: a cell's RoIAlign touches at most grid^2 * 4 * 5
-// (class, weight) pairs, which a warp accumulates into a shared-memory row of C floats; all other classes share one
-// background value exp(0 - m) / Z.  One CTA per image: pass 1 computes (m, Z) per cell, pass 2 streams the background
-// rows out (coalesced along the token dimension), pass 3 re-accumulates each cell and overwrites the touched classes.
+// (class, weight) pairs.  CTA = (image, 32 consecutive output slots): a warp owns a slot, accumulates its cell into a
+// shared-memory row of C floats (untouched classes stay 0 = the value the dense map holds there), takes the softmax over
+// the row in place (one exp per element) and applies the smoothing; the [32 slots][C] tile is then written out
+// class-major, 32 contiguous floats per class row (odd row pitch in shared memory: conflict-free transposed reads).
 #include "common.cuh"
 
 namespace {
@@ -18,6 +19,7 @@ namespace {
 constexpr int TL_THREADS = 256;
 constexpr int TL_WARPS = TL_THREADS / 32;
 constexpr int TOPK = 5;
+constexpr int TL_SLOTS = 32;   // output slots per CTA = floats per contiguous store run
 
 struct TlParams {
   const float* maps;   // [B, 3, 5, Hm, Wm]
@@ -27,10 +29,10 @@ struct TlParams {
   int softmax;
 };
 
-// accumulate the RoIAlign of output cell (ph, pw) of an (Lh x Lw)-cell pooling into vals[C]; mask marks touched classes
+// accumulate the RoIAlign of output cell (ph, pw) of an (Lh x Lw)-cell pooling into vals[C]
 __device__ __forceinline__ void accumulate_cell(const float* __restrict__ sc, const float* __restrict__ id, int Hm, int Wm, float x1,
-                                                float y1, float x2, float y2, int Lh, int Lw, int ph, int pw, float* vals,
-                                                unsigned* mask, int C, int lane) {
+                                                float y1, float x2, float y2, int Lh, int Lw, int ph, int pw, float* vals, int C,
+                                                int lane) {
   const float roi_w = fmaxf(x2 - x1, 1.f), roi_h = fmaxf(y2 - y1, 1.f);
   const float bin_h = roi_h / (float)Lh, bin_w = roi_w / (float)Lw;
   const int gh = (int)ceilf(roi_h / (float)Lh), gw = (int)ceilf(roi_w / (float)Lw);
@@ -55,18 +57,14 @@ __device__ __forceinline__ void accumulate_cell(const float* __restrict__ sc, co
     const int c = (int)id[k * plane + pix];
     if (c < 0 || c >= C) continue;
     atomicAdd(&vals[c], w * sc[k * plane + pix]);
-    atomicOr(&mask[c >> 5], 1u << (c & 31));
   }
 }
 
 __global__ void __launch_bounds__(TL_THREADS) token_label_target_kernel(TlParams p) {
-  extern __shared__ float smem_f[];
-  const int C = p.C, N = p.L * p.L, words = (C + 31) / 32;
-  float* vals_all = smem_f;                                               // [TL_WARPS][C]
-  unsigned* mask_all = reinterpret_cast<unsigned*>(vals_all + TL_WARPS * C);   // [TL_WARPS][words]
-  float* cell_m = reinterpret_cast<float*>(mask_all + TL_WARPS * words);  // [N + 1] softmax shift
-  float* cell_z = cell_m + (N + 1);                                       // [N + 1] softmax denominator
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  extern __shared__ float tile[];                                         // [TL_SLOTS][pitch]
+  const int C = p.C, N = p.L * p.L, row = 2 + N, pitch = C | 1;
+  const int b = blockIdx.y, j0 = blockIdx.x * TL_SLOTS, nslots = min(TL_SLOTS, row - j0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int plane = p.Hm * p.Wm;
   const float* sc = p.maps + (size_t)b * 3 * TOPK * plane;
   const float* id = sc + (size_t)TOPK * plane;
@@ -74,68 +72,45 @@ __global__ void __launch_bounds__(TL_THREADS) token_label_target_kernel(TlParams
   const float x1 = rec[0] * p.Wm - 0.5f, y1 = rec[1] * p.Hm - 0.5f, x2 = rec[2] * p.Wm - 0.5f, y2 = rec[3] * p.Hm - 0.5f;
   const bool flip = rec[4] > 0.5f;
   const int gt = (int)rec[5];
-  float* vals = vals_all + warp * C;
-  unsigned* mask = mask_all + warp * words;
-  float* outb = p.out + (size_t)b * C * (2 + N);
 
-  // cell n < N: token (ph, pw) of the L x L pooling (mirrored when flipped); cell N: the 1 x 1 class-level pooling
-  auto run_cell = [&](int n) {
+  // slot 0: smoothed one-hot of the ground truth; slot 1: the 1 x 1 class-level pooling; slot 2 + n: token n = (ph, pw) of
+  // the L x L pooling (mirrored when flipped)
+  for (int jj = warp; jj < nslots; jj += TL_WARPS) {
+    const int j = j0 + jj;
+    float* vals = tile + jj * pitch;
+    if (j == 0) {
+      for (int c = lane; c < C; c += 32) vals[c] = (c == gt) ? p.on : p.off;
+      continue;
+    }
     for (int c = lane; c < C; c += 32) vals[c] = 0.f;
-    for (int w = lane; w < words; w += 32) mask[w] = 0u;
     __syncwarp();
-    if (n < N) {
-      const int ph = n / p.L, pw_out = n % p.L, pw = flip ? p.L - 1 - pw_out : pw_out;
-      accumulate_cell(sc, id, p.Hm, p.Wm, x1, y1, x2, y2, p.L, p.L, ph, pw, vals, mask, C, lane);
+    if (j == 1) {
+      accumulate_cell(sc, id, p.Hm, p.Wm, x1, y1, x2, y2, 1, 1, 0, 0, vals, C, lane);
     } else {
-      accumulate_cell(sc, id, p.Hm, p.Wm, x1, y1, x2, y2, 1, 1, 0, 0, vals, mask, C, lane);
+      const int n = j - 2, ph = n / p.L, pw_out = n % p.L, pw = flip ? p.L - 1 - pw_out : pw_out;
+      accumulate_cell(sc, id, p.Hm, p.Wm, x1, y1, x2, y2, p.L, p.L, ph, pw, vals, C, lane);
     }
     __syncwarp();
-  };
-
-  // ---- pass 1: softmax statistics per cell
-  for (int n = warp; n <= N; n += TL_WARPS) {
-    run_cell(n);
-    float m = 0.f;                                   // untouched classes sit at 0
-    int touched = 0;
-    for (int c = lane; c < C; c += 32)
-      if (mask[c >> 5] & (1u << (c & 31))) { m = fmaxf(m, vals[c]); ++touched; }
-    m = warp_max(m);
-    float z = 0.f;
-    for (int c = lane; c < C; c += 32)
-      if (mask[c >> 5] & (1u << (c & 31))) z += __expf(vals[c] - m);
-    z = warp_sum(z);
-    touched = (int)warp_sum((float)touched);
-    z += (float)(C - touched) * __expf(-m);
-    if (lane == 0) { cell_m[n] = m; cell_z[n] = z; }
-    __syncwarp();
-  }
-  __syncthreads();
-  // ---- pass 2: background rows, coalesced along the slot dimension
-  const int row = 2 + N;
-  for (int i = tid; i < C * row; i += TL_THREADS) {
-    const int c = i / row, j = i % row;
-    float v;
-    if (j == 0) v = (c == gt) ? p.on : p.off;
-    else {
-      const int n = (j == 1) ? N : j - 2;
-      const float bg = p.softmax ? __expf(-cell_m[n]) / cell_z[n] : 0.f;
-      v = bg * p.on + p.off;
-    }
-    outb[i] = v;
-  }
-  __syncthreads();
-  // ---- pass 3: touched classes
-  for (int n = warp; n <= N; n += TL_WARPS) {
-    run_cell(n);
-    const float m = cell_m[n], inv_z = 1.f / cell_z[n];
-    const int j = (n == N) ? 1 : 2 + n;
-    for (int c = lane; c < C; c += 32)
-      if (mask[c >> 5] & (1u << (c & 31))) {
-        const float v = p.softmax ? __expf(vals[c] - m) * inv_z : vals[c];
-        outb[(size_t)c * row + j] = v * p.on + p.off;
+    if (p.softmax) {
+      float m = 0.f;                                   // classes the RoI never touched sit at 0
+      for (int c = lane; c < C; c += 32) m = fmaxf(m, vals[c]);
+      m = warp_max(m);
+      float z = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float e = __expf(vals[c] - m);
+        vals[c] = e;
+        z += e;
       }
-    __syncwarp();
+      const float scale = p.on / warp_sum(z);
+      for (int c = lane; c < C; c += 32) vals[c] = fmaf(vals[c], scale, p.off);
+    } else {
+      for (int c = lane; c < C; c += 32) vals[c] = fmaf(vals[c], p.on, p.off);
+    }
   }
+  __syncthreads();
+  float* outb = p.out + (size_t)b * C * row + j0;
+  if (lane < nslots)
+    for (int c = warp; c < C; c += TL_WARPS) outb[(size_t)c * row + lane] = tile[lane * pitch + c];
 }
 
 __global__ void onehot_smooth_kernel(const long long* __restrict__ labels, float* __restrict__ out, int B, int C, float on, float off) {
@@ -158,12 +133,12 @@ int apb_token_label_target(const float* maps, float* out, int B, int C, int Hm, 
   p.off = smoothing / (float)C;
   p.on = 1.f - smoothing + p.off;
   p.softmax = apply_softmax;
-  const int N = label_size * label_size, words = (C + 31) / 32;
-  const size_t smem = (size_t)TL_WARPS * C * 4 + (size_t)TL_WARPS * words * 4 + (size_t)2 * (N + 1) * 4;
-  APB_CHECK_ARG(smem <= 227 * 1024, APB_ERR_UNSUPPORTED, "token_label_target: C=%d L=%d needs %zu B of shared memory", C, label_size, smem);
+  const int row = 2 + label_size * label_size;
+  const size_t smem = (size_t)TL_SLOTS * (C | 1) * 4;
+  APB_CHECK_ARG(smem <= 227 * 1024, APB_ERR_UNSUPPORTED, "token_label_target: C=%d needs %zu B of shared memory", C, smem);
   cudaError_t e = cudaFuncSetAttribute(token_label_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { apb_set_error("token_label_target: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-  token_label_target_kernel<<<B, TL_THREADS, smem, st>>>(p);
+  token_label_target_kernel<<<dim3(ceil_div(row, TL_SLOTS), B), TL_THREADS, smem, st>>>(p);
   APB_LAUNCH_CHECK("token_label_target");
   return 0;
 }

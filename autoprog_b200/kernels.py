@@ -426,6 +426,15 @@ def launch_count() -> int:
     return int(lib().apb_launch_count())
 
 
+def set_pdl(on: bool) -> None:
+    """Programmatic dependent launch of the hot kernels (off by default; see include/autoprog_b200.h)."""
+    lib().apb_set_pdl(int(bool(on)))
+
+
+def get_pdl() -> bool:
+    return bool(lib().apb_get_pdl())
+
+
 def fallback_count() -> int:
     """bf16 calls that a tensor-core kernel declined and a CUDA-core kernel served (each one is also logged on stderr)."""
     return int(lib().apb_fallback_count())

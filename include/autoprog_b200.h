@@ -236,6 +236,12 @@ long long apb_launch_count(void);
  * CUDA-core kernel instead; each one also prints a line on stderr.  bench.py asserts / reports it (must stay 0 on the
  * benchmark configurations). */
 long long apb_fallback_count(void);
+/* programmatic dependent launch: the hot kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization so
+ * that their prologue overlaps the previous kernel's tail (each one executes griddepcontrol.wait before its first
+ * global-memory access).  Off by default (saves 0.7-1.6 us per launch in chains of one kernel, neutral on the whole
+ * training step); APB_PDL=1 in the environment or apb_set_pdl(1) turns it on. */
+void apb_set_pdl(int on);
+int apb_get_pdl(void);
 
 /* diagnostic (tools/umma_probe.py): D[128,32] = A[128,64] * B[64, off:off+32] through ONE descriptor convention
  * (mode 0..3, see csrc/umma_probe.cu); pins the shared-memory layouts the attention kernels rely on. */

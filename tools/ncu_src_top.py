@@ -5,7 +5,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 hdr = rows[1]
 ia, isrc, iall, inot, iex = hdr.index('Address'), hdr.index('Source'), hdr.index('Warp Stall Sampling (All Samples)'), hdr.index('Warp Stall Sampling (Not-issued Samples)'), hdr.index('Instructions Executed')
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith('stall_') and 'not_issued' not in h.lower()]
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) > iall and r[iall].isdigit()]
 tot = sum(int(r[iall]) for r in data)
 print('total samples', tot, 'instructions', len(data))
 ops = collections.Counter()
