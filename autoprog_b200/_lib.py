@@ -20,6 +20,8 @@ SIGNATURES = {
     'apb_outlook_bwd_simt': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     'apb_outlook_fwd_fma': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_outlook_fwd_mma': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    'apb_outlook_bwd_fma': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
+    'apb_outlook_bwd_mma': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_outlook_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     'apb_outlook_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     'apb_tlce_workspace_floats': (_ll, [_i, _i]),

@@ -2,8 +2,6 @@
 #include "common.cuh"
 
 
-int apb_outlook_bwd_mma(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
-                        int heads, float scale, int lpitch, cudaStream_t st);
 
 // bf16 -> tensor-core kernels (outlook_mma.cu); fp32, or shapes whose band does not fit shared memory -> SIMT kernels
 int apb_outlook_fwd(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int lpitch,
@@ -26,7 +24,10 @@ int apb_outlook_bwd(const void* v, const void* logits, const void* dy, void* dv,
                     int heads, float scale, int lpitch, int dtype, apb_stream_t stream) {
   if (dtype == APB_BF16 && B > 0 && H > 0 && W > 0 && heads > 0 && lpitch >= heads * 81 && lpitch < heads * 81 + 8 &&
       (((uintptr_t)v | (uintptr_t)dy | (uintptr_t)dv) & 15) == 0) {
-    const int rc = apb_outlook_bwd_mma(v, logits, dy, dv, dlogits, B, H, W, heads, scale, lpitch, APB_STREAM(stream));
+    // gather kernel first (outlook_bwd_fma.cu), the band kernel (outlook_mma.cu) covers the tiles it declines
+    int rc = apb_outlook_bwd_fma(v, logits, dy, dv, dlogits, B, H, W, heads, scale, lpitch, stream);
+    if (rc != APB_ERR_UNSUPPORTED) return rc;
+    rc = apb_outlook_bwd_mma(v, logits, dy, dv, dlogits, B, H, W, heads, scale, lpitch, stream);
     if (rc != APB_ERR_UNSUPPORTED) return rc;
   }
   if (dtype == APB_BF16) apb_note_fallback("outlook_bwd", "shape / alignment outside the tensor-core kernel's envelope");

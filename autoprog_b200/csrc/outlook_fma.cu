@@ -53,10 +53,15 @@ struct OfParams {
   int xtiles;       // ceil(w / tcw)
 };
 
+// CH > 0: heads (and the padded logits pitch that goes with it) are compile-time constants -- the kernel is issue-bound and
+// every index split by a runtime head count costs a ~20-instruction integer division (CH = 0: fully dynamic)
+template <int CH>
 __global__ void __launch_bounds__(FMA_THREADS) outlook_fwd_fma_kernel(OfParams p) {
+  const int heads = CH > 0 ? CH : p.heads;
+  const int lpitch = CH > 0 ? (CH * 81 + 7) / 8 * 8 : p.lpitch;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int C = p.heads * HD;
+  const int C = heads * HD;
   const int xt = blockIdx.x % p.xtiles;
   const int r = (blockIdx.x / p.xtiles) % p.h;            // output rows 2r, 2r+1 ; window rows r, r+1
   const int b = blockIdx.x / (p.xtiles * p.h);
@@ -68,7 +73,7 @@ __global__ void __launch_bounds__(FMA_THREADS) outlook_fwd_fma_kernel(OfParams p
   bf16* band = reinterpret_cast<bf16*>(smem_raw);
   const size_t band_bytes = ((size_t)5 * BW * C * sizeof(bf16) + 15) & ~(size_t)15;
   float* wts = reinterpret_cast<float*>(smem_raw + band_bytes);
-  const size_t wts_bytes = (size_t)nwin * p.heads * 9 * WP * sizeof(float);
+  const size_t wts_bytes = (size_t)nwin * heads * 9 * WP * sizeof(float);
   bf16* raw = reinterpret_cast<bf16*>(smem_raw + band_bytes + wts_bytes);
 
   // ---- stage 1a: pixel band (rows 2r-1 .. 2r+3, columns 2jb-1 .. ), zeros outside the image.  No divisions in the loop:
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(FMA_THREADS) outlook_fwd_fma_kernel(OfParams p
   }
   // ---- stage 1b: raw logits rows of windows (r, jb ..) and (r+1, jb ..): lpitch * 2 / 16 vectors per window
   {
-    const int vpw = p.lpitch / 8;
+    const int vpw = lpitch / 8;
     const int step_w = FMA_THREADS / vpw, step_v = FMA_THREADS % vpw;
     int wi = tid / vpw, vv = tid % vpw;                   // wi = slot * nwin + jl
     const uint32_t raw_s = smem_u32f(raw);
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(FMA_THREADS) outlook_fwd_fma_kernel(OfParams p
       const int slot = wi >= nwin ? 1 : 0, jl = wi - slot * nwin;
       const int iw = r + slot, jw = jb + jl;
       const bool ok = iw < p.h && jw < p.w;
-      const bf16* src = ok ? p.logits + (((size_t)b * p.h + iw) * p.w + jw) * p.lpitch + vv * 8 : p.logits;
+      const bf16* src = ok ? p.logits + (((size_t)b * p.h + iw) * p.w + jw) * lpitch + vv * 8 : p.logits;
       cp_async16(raw_s + (uint32_t)((wi * vpw + vv) * 16), src, ok ? 16 : 0);
       wi += step_w;
       vv += step_v;
@@ -116,17 +121,17 @@ __global__ void __launch_bounds__(FMA_THREADS) outlook_fwd_fma_kernel(OfParams p
   // ---- stage 2: thread = (window-head, weight row): 9 raw logits -> softmax -> fp32 weight row (rows of windows outside the
   //      grid become zeros).  Weight rows 0..5 = window row r, P = 3..8; rows 6..8 = window row r+1, P = 0..2
   {
-    const int nwh = nwin * p.heads;
+    const int nwh = nwin * heads;
     for (int e = tid; e < nwh * 9; e += FMA_THREADS) {
       const int ridx = e % 9, wh = e / 9;
-      const int jl = wh / p.heads, hd = wh - jl * p.heads;
+      const int jl = wh / heads, hd = wh - jl * heads;
       const int slot = ridx >= 6 ? 1 : 0, P = slot ? ridx - 6 : ridx + 3;
       const int iw = r + slot, jw = jb + jl;
       float* row = wts + (size_t)e * WP;
       float4 a, c4;
       float l8;
       if (iw < p.h && jw < p.w) {
-        const bf16* src = raw + (size_t)(slot * nwin + jl) * p.lpitch + hd * 81 + P * 9;
+        const bf16* src = raw + (size_t)(slot * nwin + jl) * lpitch + hd * 81 + P * 9;
         float q[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) q[i] = __bfloat162float(src[i]) * p.scale;
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(FMA_THREADS) outlook_fwd_fma_kernel(OfParams p
   }
   __syncthreads();
   // ---- stage 3: one warp per (output block, head pair)
-  const int npairs = (p.heads + 1) >> 1;
+  const int npairs = (heads + 1) >> 1;
   const int items = nblk * npairs;
   const int half = lane >> 4, cp = lane & 15;
   const uint32_t band_a = smem_u32f(band), wts_a = smem_u32f(wts);
@@ -155,8 +160,8 @@ __global__ void __launch_bounds__(FMA_THREADS) outlook_fwd_fma_kernel(OfParams p
   for (int item = warp; item < items; item += FMA_THREADS / 32) {
     const int hp = item % npairs, jl = item / npairs;
     const int hd = 2 * hp + half;
-    const bool head_ok = hd < p.heads;
-    const int hdc = head_ok ? hd : p.heads - 1;           // clamp: lanes of a missing head compute on valid memory, never store
+    const bool head_ok = hd < heads;
+    const int hdc = head_ok ? hd : heads - 1;           // clamp: lanes of a missing head compute on valid memory, never store
     // 5 x 5 pixel patch at band rows 0..4, band columns 2 jl .. 2 jl + 4 ; this lane's channel pair
     float v0[25], v1[25];
     {
@@ -180,8 +185,8 @@ __global__ void __launch_bounds__(FMA_THREADS) outlook_fwd_fma_kernel(OfParams p
     //   window (r, j+1)  : P=(1,0)->o1 (ridx 0), (2,0)->o3 (ridx 3);                                        origin (0,2)
     //   window (r+1, j)  : P=(0,1)->o2 (ridx 7), (0,2)->o3 (ridx 8);                                        origin (2,0)
     //   window (r+1, j+1): P=(0,0)->o3 (ridx 6);                                                            origin (2,2)
-    const uint32_t wbase = wts_a + (uint32_t)((((jl * p.heads + hdc) * 9) * WP) * 4);
-    const uint32_t wnext = (uint32_t)(p.heads * 9 * WP * 4);          // next window column
+    const uint32_t wbase = wts_a + (uint32_t)((((jl * heads + hdc) * 9) * WP) * 4);
+    const uint32_t wnext = (uint32_t)(heads * 9 * WP * 4);          // next window column
     auto apply = [&](int dj, int ridx, int oy, int ox, int o) {
       const uint32_t ra = wbase + dj * wnext + (uint32_t)(ridx * WP * 4);
       const float4 wa = lds128f(ra), wb = lds128f(ra + 16);
@@ -248,14 +253,23 @@ int apb_outlook_fwd_fma(const void* v, const void* logits, void* y, int B, int H
   p.xtiles = ceil_div(p.w, tcw);
   p.tcw = ceil_div(p.w, p.xtiles);
   const size_t smem = smem_for(p.tcw);
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(outlook_fwd_fma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { apb_set_error("outlook_fwd_fma: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    attr = smem;
-  }
   const long long grid = (long long)B * p.h * p.xtiles;
-  outlook_fwd_fma_kernel<<<(unsigned)grid, FMA_THREADS, smem, st>>>(p);
+  const int ch = (heads == 6 || heads == 8 || heads == 12) && lpitch == (heads * 81 + 7) / 8 * 8 ? heads : 0;
+#define OL_LAUNCH(CH_)                                                                                                      \
+  do {                                                                                                                      \
+    static size_t attr = 0;                                                                                                 \
+    if (smem > attr) {                                                                                                      \
+      cudaError_t e = cudaFuncSetAttribute(outlook_fwd_fma_kernel<CH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) { apb_set_error("outlook_fwd_fma_kernel: smem attr: %s", cudaGetErrorString(e)); return (int)e; }  \
+      attr = smem;                                                                                                          \
+    }                                                                                                                       \
+    outlook_fwd_fma_kernel<CH_><<<(unsigned)grid, FMA_THREADS, smem, st>>>(p);                                                 \
+  } while (0)
+  if (ch == 6) OL_LAUNCH(6);
+  else if (ch == 8) OL_LAUNCH(8);
+  else if (ch == 12) OL_LAUNCH(12);
+  else OL_LAUNCH(0);
+#undef OL_LAUNCH
   APB_LAUNCH_CHECK("outlook_fwd_fma");
   return 0;
 }

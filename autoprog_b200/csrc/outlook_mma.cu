@@ -463,7 +463,8 @@ int apb_outlook_fwd_mma(const void* v, const void* logits, void* y, int B, int H
 }
 
 int apb_outlook_bwd_mma(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
-                        int heads, float scale, int lpitch, cudaStream_t st) {
+                        int heads, float scale, int lpitch, apb_stream_t stream) {
+  cudaStream_t st = APB_STREAM(stream);
   Geo g = make_geo(B, H, W, heads, scale, lpitch);
   size_t smem;
   if (plan(g, true, smem) != 0) return APB_ERR_UNSUPPORTED;

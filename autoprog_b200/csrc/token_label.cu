@@ -16,7 +16,7 @@
 
 namespace {
 
-constexpr int TL_THREADS = 256;
+constexpr int TL_THREADS = 512;
 constexpr int TL_WARPS = TL_THREADS / 32;
 constexpr int TOPK = 5;
 constexpr int TL_SLOTS = 32;   // output slots per CTA = floats per contiguous store run
@@ -61,18 +61,22 @@ __device__ __forceinline__ void accumulate_cell(const float* __restrict__ sc, co
 }
 
 __global__ void __launch_bounds__(TL_THREADS) token_label_target_kernel(TlParams p) {
-  extern __shared__ float tile[];                                         // [TL_SLOTS][pitch]
+  extern __shared__ float tile[];                                         // [TL_SLOTS][pitch] | scores + ids [2][5][plane]
   const int C = p.C, N = p.L * p.L, row = 2 + N, pitch = C | 1;
   const int b = blockIdx.y, j0 = blockIdx.x * TL_SLOTS, nslots = min(TL_SLOTS, row - j0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int plane = p.Hm * p.Wm;
-  const float* sc = p.maps + (size_t)b * 3 * TOPK * plane;
-  const float* id = sc + (size_t)TOPK * plane;
-  const float* rec = id + (size_t)TOPK * plane;
+  const float* gsc = p.maps + (size_t)b * 3 * TOPK * plane;
+  const float* rec = gsc + (size_t)2 * TOPK * plane;
+  // the image's top-5 score and id planes -> shared memory once (the RoIAlign taps are data-dependent gathers)
+  float* sc = tile + TL_SLOTS * pitch;
+  const float* id = sc + TOPK * plane;
+  for (int i = tid; i < 2 * TOPK * plane; i += TL_THREADS) sc[i] = gsc[i];
   const float x1 = rec[0] * p.Wm - 0.5f, y1 = rec[1] * p.Hm - 0.5f, x2 = rec[2] * p.Wm - 0.5f, y2 = rec[3] * p.Hm - 0.5f;
   const bool flip = rec[4] > 0.5f;
   const int gt = (int)rec[5];
 
+  __syncthreads();
   // slot 0: smoothed one-hot of the ground truth; slot 1: the 1 x 1 class-level pooling; slot 2 + n: token n = (ph, pw) of
   // the L x L pooling (mirrored when flipped)
   for (int jj = warp; jj < nslots; jj += TL_WARPS) {
@@ -134,7 +138,7 @@ int apb_token_label_target(const float* maps, float* out, int B, int C, int Hm, 
   p.on = 1.f - smoothing + p.off;
   p.softmax = apply_softmax;
   const int row = 2 + label_size * label_size;
-  const size_t smem = (size_t)TL_SLOTS * (C | 1) * 4;
+  const size_t smem = (size_t)TL_SLOTS * (C | 1) * 4 + (size_t)2 * 5 * Hm * Wm * 4;
   APB_CHECK_ARG(smem <= 227 * 1024, APB_ERR_UNSUPPORTED, "token_label_target: C=%d needs %zu B of shared memory", C, smem);
   cudaError_t e = cudaFuncSetAttribute(token_label_target_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { apb_set_error("token_label_target: smem attr: %s", cudaGetErrorString(e)); return (int)e; }

@@ -49,6 +49,13 @@ int apb_outlook_fwd_fma(const void* v, const void* logits, void* y, int B, int H
                         apb_stream_t stream);
 int apb_outlook_fwd_mma(const void* v, const void* logits, void* y, int B, int H, int W, int heads, float scale, int lpitch,
                         apb_stream_t stream);
+/* the two bf16 backward kernels behind apb_outlook_bwd: `_fma` = one kernel, dV as the forward's gather with transposed
+ * weights + dlogits as a 16x16x32 mma.sync product per (window, head) (outlook_bwd_fma.cu); `_mma` = the band kernel of
+ * outlook_mma.cu.  Both return APB_ERR_UNSUPPORTED when their tile does not fit shared memory. */
+int apb_outlook_bwd_fma(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
+                        int heads, float scale, int lpitch, apb_stream_t stream);
+int apb_outlook_bwd_mma(const void* v, const void* logits, const void* dy, void* dv, void* dlogits, int B, int H, int W,
+                        int heads, float scale, int lpitch, apb_stream_t stream);
 /* lpitch: elements between consecutive windows in logits/dlogits, heads*81 <= lpitch < heads*81+8.  The bf16 path
  * pads 486 -> 488 so the producing / consuming GEMMs satisfy TMA's 16-byte row pitch; backward zero-fills the pad. */
 

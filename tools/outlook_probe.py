@@ -22,9 +22,11 @@ for HW in (28, 24, 20, 16):
     s = 32 ** -0.5
     tf = t(lambda i: lib().apb_outlook_fwd_fma(vs[i].data_ptr(), lg.data_ptr(), y.data_ptr(), B, HW, HW, 6, s, 488, st()))
     tm = t(lambda i: lib().apb_outlook_fwd_mma(vs[i].data_ptr(), lg.data_ptr(), y.data_ptr(), B, HW, HW, 6, s, 488, st()))
-    tb = t(lambda i: K.outlook_bwd(vs[i], lg, dy, 6, s))
+    dv = torch.empty_like(vs[0]); dl = torch.empty_like(lg)
+    tb = t(lambda i: lib().apb_outlook_bwd_fma(vs[i].data_ptr(), lg.data_ptr(), dy.data_ptr(), dv.data_ptr(), dl.data_ptr(), B, HW, HW, 6, s, 488, st()))
+    tbm = t(lambda i: lib().apb_outlook_bwd_mma(vs[i].data_ptr(), lg.data_ptr(), dy.data_ptr(), dv.data_ptr(), dl.data_ptr(), B, HW, HW, 6, s, 488, st()))
     fby = (2 * vs[0].numel() + B * h * h * 486) * 2; bby = (3 * vs[0].numel() + 2 * B * h * h * 486) * 2
-    print(f'outlook B={B} {HW}x{HW}x192: fwd fma {tf:.1f} us ({fby / tf / 1e3:.0f} GB/s)  fwd mma {tm:.1f} us  bwd {tb:.1f} us ({bby / tb / 1e3:.0f} GB/s)', flush=True)
+    print(f'outlook B={B} {HW}x{HW}x192: fwd fma {tf:.1f} us ({fby / tf / 1e3:.0f} GB/s)  fwd mma {tm:.1f} us  bwd fma {tb:.1f} us ({bby / tb / 1e3:.0f} GB/s)  bwd mma {tbm:.1f} us', flush=True)
 xa = torch.randn(B, 196, 1000, device=dev).to(bf); xc = torch.randn(B, 1000, device=dev).to(bf); tg = torch.softmax(torch.randn(B, 1000, 198, device=dev), 1)
 tt = t(lambda i: K.tlce_fwd_bwd(xc, xa, tg, 4, 1.0, 0.5))
 print(f'tlce B=128 N=196 C=1000 bf16: {tt:.1f} us ({xa.numel() * 8 / tt / 1e3:.0f} GB/s)')
