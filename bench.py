@@ -35,6 +35,27 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE line, the JSON result: fd 1 is pointed at stderr for the whole run (libraries such as NCCL print
+# banners on stdout) and the saved descriptor is used only by emit()
+_RESULT_FD = None
+
+
+def claim_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
+
 WORKLOAD = 'volo_d1 (== volo_h12_l18) AutoProg final stage: 224px, depth 18, per-GPU batch 128, bf16, TokenLabelCE(dense 0.5)'
 EMA_DECAYS = [0.998, 0.9986, 0.999, 0.9996]            # scripts/train_autoprog.sh
 STAGES = ((9, 128, 0.0), (12, 160, 0.1 / 3), (15, 192, 0.2 / 3), (18, 224, 0.1))   # progressive_schedule of the shipped script
@@ -113,7 +134,7 @@ def run_reference(args):
         'cpu_baseline': {'value': round(v, 3), 'unit': 'images/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': round(v, 3), 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -487,7 +508,7 @@ def run_headline(env, args, spec):
     line.update(extra)
     if stages is not None:
         line['autoprog_stages'] = stages
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def stage_table(env, args, K, last=None):
@@ -569,7 +590,7 @@ def run_stages(env, args):
                                    'harmonic mean over the four equal-length stages', 'parallelism': f'dp{env.world}'},
             'autoprog_stages': rows, 'supernet_epoch': supernet,
             'schedule_speedup_vs_full_model': round(value / full, 3) if full else None}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_deit(env, args):
@@ -599,12 +620,12 @@ def run_deit(env, args):
     value = len(ok) / sum(1.0 / r['images_per_s'] for r in ok) if ok else 0.0
     if env.rank != 0:
         return
-    print(json.dumps({'metric': 'train images/sec', 'value': round(value, 1), 'unit': 'images/s', 'n_gpus': env.world, 'steps': args.steps,
+    emit({'metric': 'train images/sec', 'value': round(value, 1), 'unit': 'images/s', 'n_gpus': env.world, 'steps': args.steps,
                       'warmup': 3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
                       'config': {'workload': 'deit_small (D=384, 12 layers, 6 heads x 64) progressive: elastic depth l6..12 at r128..224, '
                                              'token-label aux head + TokenLabelCE(dense 0.5), per-GPU batch 128, bf16, fused AdamW + 4 EMA; '
                                              'value = harmonic mean over the four stages', 'parallelism': f'dp{env.world}'},
-                      'stages': rows}), flush=True)
+                      'stages': rows})
 
 
 def run_micro(env, args):
@@ -683,15 +704,17 @@ def run_micro(env, args):
             torch.cuda.empty_cache()
             rows.append(row)
     head = next((x for x in rows if x['r'] == 224 and x['B'] == 128 and 'outlook_gbs' in x), None)
-    print(json.dumps({'metric': 'OutlookAttention fwd+bwd HBM GB/s', 'value': head['outlook_gbs'] if head else None, 'unit': 'GB/s',
+    emit({'metric': 'OutlookAttention fwd+bwd HBM GB/s', 'value': head['outlook_gbs'] if head else None, 'unit': 'GB/s',
                       'n_gpus': 1, 'higher_is_better': True, 'dtype': 'bf16', 'data': 'synthetic', 'vs_baseline': None,
                       'config': {'workload': 'OutlookAttention core (C=192, 6 heads) + TokenLabelCrossEntropy (C=1000) fwd+bwd sweep, '
                                              'r in 112..448, B in 64..512; value = the r224 / B128 cell; reference = oracle torch ops on this GPU'},
-                      'peak_hbm_gbs': peaks['hbm_gbs'], 'peak_source': peaks['src'], 'cells': rows}), flush=True)
+                      'peak_hbm_gbs': peaks['hbm_gbs'], 'peak_source': peaks['src'], 'cells': rows})
 
 
 def main():
     args = parse()
+    if not (args.gpus > 1 and 'RANK' not in os.environ):      # (the torchrun re-launcher passes its children's stdout through)
+        claim_stdout()
     if args.impl == 'reference':
         run_reference(args)
         return
