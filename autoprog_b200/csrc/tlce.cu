@@ -297,6 +297,68 @@ __global__ void __launch_bounds__(NTHREADS, 2) tlce_fast_kernel(TlceParams p) {
 }
 
 // deterministic final reduction of the per-CTA partials (fixed tree order)
+// Class-token part of the fast path: one CTA per image, thread = classes tid, tid + 256, ...  The class-level labels sit
+// at stride (2 + N) floats in the class-major target, i.e. every load is its own sector: all of a thread's loads (own image
+// and, when mixing, the flipped image) are issued before the first use and kept in registers for the gradient pass -- the
+// warp-per-image loop this replaces walked 2 x 32 dependent strided loads per lane (32 us for 128 images).
+constexpr int CLS_MAXJ = 4;            // classes per thread (C <= 1024)
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS) tlce_cls_kernel(TlceParams p, int partial_base) {
+  __shared__ float red[3][NTHREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x, C = p.C;
+  const T* xr = reinterpret_cast<const T*>(p.x_cls) + (size_t)b * C;
+  T* dr = reinterpret_cast<T*>(p.d_cls) + (size_t)b * C;
+  const float* t0 = p.target + (size_t)b * p.t_sb + (size_t)p.slot_cls * p.t_ss;
+  const float* t1 = p.target + (size_t)(p.B - 1 - b) * p.t_sb + (size_t)p.slot_cls * p.t_ss;
+  float lam = p.lam;
+  if (p.box_dev != nullptr) lam = 1.f - (float)((p.box_dev[2] - p.box_dev[0]) * (p.box_dev[3] - p.box_dev[1])) / (float)p.N;
+  const bool mix = lam < 1.f;
+  float x[CLS_MAXJ], t[CLS_MAXJ], u[CLS_MAXJ];
+#pragma unroll
+  for (int j = 0; j < CLS_MAXJ; ++j) {
+    const int c = tid + j * NTHREADS;
+    const bool ok = c < C;
+    x[j] = ok ? to_f(xr[c]) : -INFINITY;
+    t[j] = ok ? t0[(size_t)c * p.t_sc] : 0.f;
+    u[j] = (ok && mix) ? t1[(size_t)c * p.t_sc] : 0.f;
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < CLS_MAXJ; ++j) {
+    if (mix) t[j] = lam * t[j] + (1.f - lam) * u[j];
+    m = fmaxf(m, x[j]);
+  }
+  m = warp_max(m);
+  if (lane == 0) red[0][warp] = m;
+  __syncthreads();
+  m = red[0][0];
+#pragma unroll
+  for (int i = 1; i < NTHREADS / 32; ++i) m = fmaxf(m, red[0][i]);
+  __syncthreads();
+  float se = 0.f, sum_t = 0.f, sum_tx = 0.f;
+#pragma unroll
+  for (int j = 0; j < CLS_MAXJ; ++j)
+    if (tid + j * NTHREADS < C) {
+      se += expf(x[j] - m);
+      sum_t += t[j];
+      sum_tx = fmaf(t[j], x[j], sum_tx);
+    }
+  se = warp_sum(se); sum_t = warp_sum(sum_t); sum_tx = warp_sum(sum_tx);
+  if (lane == 0) { red[0][warp] = se; red[1][warp] = sum_t; red[2][warp] = sum_tx; }
+  __syncthreads();
+  se = sum_t = sum_tx = 0.f;
+#pragma unroll
+  for (int i = 0; i < NTHREADS / 32; ++i) { se += red[0][i]; sum_t += red[1][i]; sum_tx += red[2][i]; }     // fixed order
+  const float lse = m + logf(se);
+#pragma unroll
+  for (int j = 0; j < CLS_MAXJ; ++j) {
+    const int c = tid + j * NTHREADS;
+    if (c < C) dr[c] = from_f<T>(p.w_cls * (expf(x[j] - lse) * sum_t - t[j]));
+  }
+  if (tid == 0) p.partial[partial_base + b] = p.w_cls * (lse * sum_t - sum_tx);
+}
+
 __global__ void __launch_bounds__(256) tlce_reduce_kernel(const float* __restrict__ partial, int n, float* loss) {
   __shared__ double s[256];
   double acc = 0.0;
@@ -321,7 +383,7 @@ __global__ void scale_by_scalar_kernel(const T* __restrict__ in, T* __restrict__
 
 // workspace: floats, at least apb_tlce_workspace_floats(B, N) entries.
 long long apb_tlce_workspace_floats(int B, int N) {
-  return (long long)B * ((N + TT - 1) / TT) + (B + NTHREADS / 32 - 1) / (NTHREADS / 32);
+  return (long long)B * ((N + TT - 1) / TT) + B;      // dense tiles + one class-token partial per image (fast path)
 }
 
 int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, int target_is_3d, int B, int N, int C,
@@ -361,11 +423,10 @@ int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, 
       tlce_fast_kernel<bf16><<<n_aux, NTHREADS, fsmem, st>>>(p);
     }
     APB_LAUNCH_CHECK("tlce_fast_kernel");
-    p.cta_offset = n_aux;                      // class-token CTAs only
-    if (dtype == APB_F32) tlce_kernel<float><<<n_cls_ctas, NTHREADS, 0, st>>>(p);
-    else tlce_kernel<bf16><<<n_cls_ctas, NTHREADS, 0, st>>>(p);
-    APB_LAUNCH_CHECK("tlce_kernel(cls)");
-    tlce_reduce_kernel<<<1, 256, 0, st>>>(workspace, grid, loss);
+    if (dtype == APB_F32) tlce_cls_kernel<float><<<B, NTHREADS, 0, st>>>(p, n_aux);
+    else tlce_cls_kernel<bf16><<<B, NTHREADS, 0, st>>>(p, n_aux);
+    APB_LAUNCH_CHECK("tlce_cls_kernel");
+    tlce_reduce_kernel<<<1, 256, 0, st>>>(workspace, n_aux + B, loss);
     APB_LAUNCH_CHECK("tlce_reduce");
     return 0;
   }
