@@ -9,6 +9,7 @@ Backward never consults autocast state: each Function records its compute dtype 
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Optional
 
@@ -102,8 +103,36 @@ def grad_dest(p):
     return getattr(p, '_apb_grad_view', None)
 
 
+# The weight-gradient GEMM (+ its split-K reduce) of a Linear does not depend on the input-gradient GEMM: with
+# SIDE_WGRAD they are enqueued on two streams (fork on dY, join right after both are enqueued), so the CTAs of one fill
+# the SMs the other's last wave leaves idle and one launch gap per pair disappears.  The join precedes every later
+# kernel, so no tensor outlives its producer across streams; under CUDA-graph capture the fork becomes two branches.
+SIDE_WGRAD = os.environ.get('APB_SIDE_WGRAD', '1') == '1'
+_side_streams = {}
+
+
+def _side_stream(device):
+    s = _side_streams.get(device)
+    if s is None:
+        s = _side_streams[device] = torch.cuda.Stream(device=device)
+    return s
+
+
 def _lin_bwd(dy2d, x2d, w, need_dx=True, need_dw=True, need_db=True, dgelu_aux=None, dw_out=None, db_out=None):
     """Returns (dx [M,K] compute dtype, dw [N,K] fp32, db [N] fp32).  dw_out / db_out: in-place destinations."""
+    if SIDE_WGRAD and need_dx and need_dw and dy2d.is_cuda and dy2d.dtype == BF16:
+        main = torch.cuda.current_stream(dy2d.device)
+        side = _side_stream(dy2d.device)
+        side.wait_stream(main)                       # dY (and everything before it) is ready
+        dx, _, _ = _lin_bwd_impl(dy2d, x2d, w, True, False, False, dgelu_aux, None, None)
+        with torch.cuda.stream(side):
+            _, dw, db = _lin_bwd_impl(dy2d, x2d, w, False, True, need_db, None, dw_out, db_out)
+        main.wait_stream(side)
+        return dx, dw, db
+    return _lin_bwd_impl(dy2d, x2d, w, need_dx, need_dw, need_db, dgelu_aux, dw_out, db_out)
+
+
+def _lin_bwd_impl(dy2d, x2d, w, need_dx, need_dw, need_db, dgelu_aux, dw_out, db_out):
     M, N = dy2d.shape
     Kd = w.shape[1]
     dx = dw = db = None
