@@ -863,7 +863,7 @@ def measure_rooflines(train_step, x, t, K, torch, B, bf16):
         tfm = (mfw + mbw) / ((mf + mb) * 1e-3) / 1e12
         extra['roofline_mhsa'] = {'kernel': 'MHSA core fwd+bwd (tcgen05 / TMEM)', 'bound': 'tensor', 'achieved': round(tfm, 1),
                                   'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                                  'frac': round(tfm / peaks['bf16_tflops_sustained'], 4), 'layers': mn,
+                                  'frac': round(tfm / peaks['bf16_tflops_sustained'], 4), 'layers': mn, 'traffic': tr('mhsa'),
                                   'fwd_ms_per_step': round(mf, 3), 'bwd_ms_per_step': round(mb, 3),
                                   'flops': 'algorithmic 4 N^2 D per head fwd, 10 N^2 D bwd (unpadded)'}
     return roof, extra

@@ -32,12 +32,14 @@ for r in rows[hdr + 1:]:
     v *= {'byte': 1, 'kbyte': 1e3, 'mbyte': 1e6, 'gbyte': 1e9}.get(u, 1)
     per_launch.setdefault((r[ii], r[ki]), 0.0)
     per_launch[(r[ii], r[ki])] += v
-groups = {'gemm_tc': r'gemm_tc2?_kernel', 'outlook': r'outlook_(fwd|bwd)_(mma|fma)_kernel', 'tlce': r'tlce_(fast_)?kernel', 'mhsa': r'mhsa_(fwd|bwd)_tc_kernel'}
+groups = {'gemm_tc': r'gemm_tc2?_kernel', 'outlook': r'outlook_(fwd|bwd)_(mma|fma)_kernel', 'tlce': r'tlce_(fast_|cls_)?kernel',
+          'mhsa': r'mhsa_(fwd|bwd|rowdot)_tc_kernel'}
+per_op = {'tlce'}          # one op call per step = several launches: quote the step total as 'per launch'
 out = {}
 for g, pat in groups.items():
     vals = [v for (i, k), v in per_launch.items() if re.search(pat, k)]
     if vals:
-        out[g] = {'launches': len(vals), 'dram_bytes_total': sum(vals), 'dram_bytes_per_launch': sum(vals) / len(vals)}
+        out[g] = {'launches': len(vals), 'dram_bytes_total': sum(vals), 'dram_bytes_per_launch': sum(vals) / (1 if g in per_op else len(vals))}
 json.dump({'csrc_sha': sha(), 'source': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over one training step (tools/profile_step.py: '
            'volo_d1, B=128, 224 px, bf16)', 'kernels': out}, open(sys.argv[2], 'w'), indent=1)
 print(json.dumps(out, indent=1))
