@@ -785,6 +785,9 @@ def measure_rooflines(train_step, x, t, K, torch, B, bf16):
     setattr(K, 'tlce_fwd_bwd', wrap('tlce_fwd_bwd', lambda xc, xa, *a, **kw: xa.numel() * (2 * es + 4)))
     setattr(K, 'mhsa_fwd', wrap('mhsa_fwd', mhsa_work))
     setattr(K, 'mhsa_bwd', wrap('mhsa_bwd', lambda qkv, *a, **kw: 2.5 * mhsa_work(qkv)))     # 5 products vs 2
+    from autoprog_b200 import ops as _ops
+    side_wgrad = _ops.SIDE_WGRAD
+    _ops.SIDE_WGRAD = False           # event brackets need one kernel at a time: no dgrad / wgrad overlap in this extra step
     try:
         host_s = 0.05
         for it in range(3):           # first pass warms the caching allocator, second one times the host's enqueue
@@ -799,6 +802,7 @@ def measure_rooflines(train_step, x, t, K, torch, B, bf16):
             host_s = time.perf_counter() - h0
             torch.cuda.synchronize()
     finally:
+        _ops.SIDE_WGRAD = side_wgrad
         for n in names:
             setattr(K, n, orig[n])
 
