@@ -23,6 +23,7 @@
 //   * rowsum (apb_gemm_tc_rowsum): sum_k A(m,k) -- the bias gradient of a wgrad GEMM -- from one extra 128 x 16 x 16 MMA
 //     per k-step against a tile of ones, shared between the n-tiles of an m-tile.
 // The forward-shaped K >= 384 products run on CTA pairs instead (gemm_tc2.cu, cta_group::2).
+#include <stdlib.h>
 #include "gemm_tc_common.cuh"
 
 namespace {
@@ -42,6 +43,7 @@ struct TcParams {
   int kb_per_split;     // k-blocks per split
   int splits;
   int tiles_m, tiles_n;
+  int dbg;              // diagnostics (APB_GEMM_DBG, tools/gemm_bound.py): 1 = no TMA loads (stale operands), 2 = no MMAs, 4 = no stores
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -80,7 +82,9 @@ __device__ __forceinline__ float dgelu_f(float x) {
 
 // AUX = the epilogue needs the per-warp gelu' boxes (GELU / dGELU).  Without them the shared memory they would take
 // becomes one more pipeline stage: the main loop is bound by bytes in flight from L2, not by the tensor pipe.
-template <int BN, int STAGES, int EPI_WARPS, bool AUX>
+// NARROW: bf16 output, no row sums, no GELU boxes -> one 2 KB staging box per epilogue warp and no tile of ones: the 24 KB + 2 KB
+// saved hold a FIFTH pipeline stage (the k-block period is (load latency + MMA time of a stage) / STAGES, tools/gemm_bound.py)
+template <int BN, int STAGES, int EPI_WARPS, bool AUX, bool NARROW>
 __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                              const __grid_constant__ CUtensorMap tma_b,
                                                              const __grid_constant__ CUtensorMap tma_c,
@@ -90,13 +94,13 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t RS_COLS = 16;                                        // row-sum accumulator: one N = 16 MMA per k-step
   constexpr uint32_t TMEM_COLS = (ACC_STAGES * (BN + RS_COLS) <= 256) ? 256 : 512;   // power of two >= 2 accumulator stages
-  constexpr uint32_t ONES_BYTES = AUX ? 0 : 2048;                         // 16 rows x 128 B of bf16 1.0 (the "B operand" of the row sum)
+  constexpr uint32_t ONES_BYTES = (AUX || NARROW) ? 0 : 2048;                         // 16 rows x 128 B of bf16 1.0 (the "B operand" of the row sum)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // per epilogue warp: C boxes (AUX kernels write bf16 only: one 2 KB box per chunk; otherwise 4 KB so that the single
   // 32 x 128 B fp32 box fits) + one 2 KB gelu' box per chunk
   constexpr uint32_t NCH_ = (BN / 32) / (EPI_WARPS / 4);
-  constexpr uint32_t STGC_BYTES = AUX ? NCH_ * 2048 : 4096;
+  constexpr uint32_t STGC_BYTES = AUX ? NCH_ * 2048 : (NARROW ? 2048 : 4096);
   constexpr uint32_t STG_BYTES = STGC_BYTES + (AUX ? NCH_ * 2048 : 0);
   uint8_t* ones = smem + STAGES * STAGE_BYTES;
   uint8_t* stg_base = ones + ONES_BYTES;
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
   const int total_kb = (p.K + BK - 1) / BK;
   const int n_items = p.tiles_m * p.tiles_n * p.splits;
 
-  if (!AUX && p.rowsum != nullptr) {
+  if (!AUX && !NARROW && p.rowsum != nullptr) {
     for (int i = threadIdx.x; i < (int)(ONES_BYTES / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA's async proxy
   }
@@ -150,7 +154,9 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         uint8_t* sa = smem + s * STAGE_BYTES;
         uint8_t* sb = sa + A_BYTES;
         const int k0 = kb * BK;
-        if (leader) {
+        if (leader && (p.dbg & 1)) {
+          mbar_expect_tx(&full_bar[s], 0);
+        } else if (leader) {
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           if (!p.a_mn) {
             tma_load_2d(sa, &tma_a, &full_bar[s], k0, m0);                 // box {64 k, 128 m}
@@ -205,9 +211,10 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
           const uint64_t ad0 = make_smem_desc(sa, a_lbo, 1024), bd0 = make_smem_desc(sb, b_lbo, 1024);
           const uint32_t acc_first = kb > kb0 ? 1u : 0u;
           // two straight-line versions of the k-steps (no conditionally executed tensor-core instruction)
-          const bool with_rs = !AUX && p.rowsum != nullptr && (kb % p.tiles_n) == tn;
+          const bool with_rs = !AUX && !NARROW && p.rowsum != nullptr && (kb % p.tiles_n) == tn;
           if (leader) {
-            if (with_rs) {
+            if (p.dbg & 2) {
+            } else if (with_rs) {
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
                 umma_bf16(tacc, ad0 + k * a_kstep, bd0 + k * b_kstep, idesc, k > 0 ? 1u : acc_first);
@@ -337,12 +344,13 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
             *reinterpret_cast<uint4*>(stg64(sx, lane, ch)) = pk;
           }
         }
-        uint8_t* sc = dgelu ? sx : (p.out_f32 ? stgC : stgC + c * 2048);
+        const bool single_box = p.out_f32 || NARROW;
+        uint8_t* sc = dgelu ? sx : (single_box ? stgC : stgC + c * 2048);
+        if (single_box && c > 0) {                  // the single box is reused: wait until the previous store has read it
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        }
         if (p.out_f32) {
-          if (c > 0) {                              // the single fp32 box is reused: wait until the previous store has read it
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncwarp();
-          }
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch)
             *reinterpret_cast<float4*>(stg128(sc, lane, ch)) = make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
@@ -358,7 +366,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(p.dbg & 4)) {
           tma_store_3d(&tma_c, sc, cb, rb, z);
           if (AUX && p.epilogue == 1) tma_store_3d(&tma_x, sx, cb, rb, 0);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -382,23 +390,28 @@ int pick_bn(int N) {
   return (ceil_div(N, 192) * 192 <= ceil_div(N, 128) * 128) ? 192 : 128;
 }
 
-template <int BN, int STAGES, int EPI_WARPS, bool AUX>
+template <int BN, int STAGES, int EPI_WARPS, bool AUX, bool NARROW = false>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mx, TcParams p, int splits,
            cudaStream_t st) {
-  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + (AUX ? 0 : 2048) + EPI_WARPS * (AUX ? 2 * ((BN / 32) / (EPI_WARPS / 4)) * 2048 : 4096) + 1024 + 512;
+  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + ((AUX || NARROW) ? 0 : 2048) +
+                          EPI_WARPS * (AUX ? 2 * ((BN / 32) / (EPI_WARPS / 4)) * 2048 : (NARROW ? 2048 : 4096)) + 1024 + 512;
   static_assert(smem <= 227 * 1024, "gemm_tc: shared memory budget");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI_WARPS, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, EPI_WARPS, AUX, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { apb_set_error("gemm_tc: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
   p.tiles_m = ceil_div(p.M, BM);
   p.tiles_n = ceil_div(p.N, BN);
   p.splits = splits;
+  {
+    const char* e = getenv("APB_GEMM_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   const long long items = (long long)p.tiles_m * p.tiles_n * splits;
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  apb_launch_pdl(gemm_tc_kernel<BN, STAGES, EPI_WARPS, AUX>, dim3(grid), dim3(64 + EPI_WARPS * 32), smem, st, ma, mb, mc, mx, p);
+  apb_launch_pdl(gemm_tc_kernel<BN, STAGES, EPI_WARPS, AUX, NARROW>, dim3(grid), dim3(64 + EPI_WARPS * 32), smem, st, ma, mb, mc, mx, p);
   APB_LAUNCH_CHECK("gemm_tc");
   return 0;
 }
@@ -457,6 +470,9 @@ int apb_gemm_tc_rowsum(const void* A, const void* B, void* C, const float* bias,
   APB_CHECK_ARG(!(aux_epi && rowsum_parts != nullptr), APB_ERR_UNSUPPORTED, "gemm_tc: row sums are not available with GELU epilogues");
   if (BN == 64) return aux_epi ? launch<64, 6, 8, true>(ma, mb, mc, mx, p, splits, st) : launch<64, 6, 8, false>(ma, mb, mc, mx, p, splits, st);
   // (24 epilogue warps for the GELU kernels were measured on the same box: 19.83 vs 19.79 ms / step with 12 -> kept 12)
+  // bf16 output without row sums (forward and dgrad products): 5 stages (APB_GEMM_NARROW=0: the 4-stage kernel, for A/B runs)
+  if (BN == 192 && !aux_epi && !p.out_f32 && rowsum_parts == nullptr && splits == 1 && !(getenv("APB_GEMM_NARROW") && getenv("APB_GEMM_NARROW")[0] == '0'))
+    return launch<192, 5, 12, false, true>(ma, mb, mc, mx, p, splits, st);
   if (BN == 192) return aux_epi ? launch<192, 3, 12, true>(ma, mb, mc, mx, p, splits, st) : launch<192, 4, 12, false>(ma, mb, mc, mx, p, splits, st);
   return aux_epi ? launch<128, 4, 16, true>(ma, mb, mc, mx, p, splits, st) : launch<128, 4, 16, false>(ma, mb, mc, mx, p, splits, st);
 }

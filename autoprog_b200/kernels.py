@@ -166,9 +166,9 @@ def gemm(a, b, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = Fa
         return (out, aux) if epilogue == EPI_GELU else out
     if (_PAIR_GEMM and not trans_a and not trans_b and epilogue == EPI_NONE and rowsum_out is None and M >= 8192
             and K >= 384 and N % 192 == 0 and out_dtype in (torch.bfloat16, torch.float32)):
-        # measured (tools/gemm_shapes.py): 7-8 % faster than the one-CTA kernel on the K >= 384 forward shapes, slower
-        # on the K = 192 ones (those are bound by the output stream, not by operand traffic)
-        # forward-shaped product with a tall M: CTA-pair kernel (cta_group::2), half the B-tile traffic per SM
+        # CTA-pair kernel (cta_group::2, half the B-tile traffic per SM): opt-in (APB_GEMM_PAIR=1).  Measured in CUDA graphs
+        # (tools/gemm_shapes.py) it ties the 4-stage one-CTA kernel and loses to the 5-stage one (22.0 vs 20.1 us at
+        # 25088 x 384 x 1152): the main loop is bound by bytes in flight per SM, not by operand traffic
         check(lib().apb_gemm_tc_pair(_p(a), _p(b), _p(out), _p(bias), M, N, K, _CODES[out_dtype], _st()), 'gemm_tc_pair')
         return out
     split = 1
@@ -190,7 +190,7 @@ def gemm(a, b, M: int, N: int, K: int, trans_a: bool = False, trans_b: bool = Fa
     return (out, aux) if epilogue == EPI_GELU else out
 
 
-_PAIR_GEMM = os.environ.get('APB_GEMM_PAIR', '1') == '1'
+_PAIR_GEMM = os.environ.get('APB_GEMM_PAIR', '0') == '1'   # off: the 5-stage one-CTA kernel is faster on every shape (profiles/r2_kernels.md)
 
 
 def gemm_uses_tc(a: torch.Tensor, M: int, N: int, K: int) -> bool:
