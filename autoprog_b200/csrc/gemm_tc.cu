@@ -82,9 +82,10 @@ __device__ __forceinline__ float dgelu_f(float x) {
 
 // AUX = the epilogue needs the per-warp gelu' boxes (GELU / dGELU).  Without them the shared memory they would take
 // becomes one more pipeline stage: the main loop is bound by bytes in flight from L2, not by the tensor pipe.
-// NARROW: bf16 output, no row sums, no GELU boxes -> one 2 KB staging box per epilogue warp and no tile of ones: the 24 KB + 2 KB
-// saved hold a FIFTH pipeline stage (the k-block period is (load latency + MMA time of a stage) / STAGES, tools/gemm_bound.py)
-template <int BN, int STAGES, int EPI_WARPS, bool AUX, bool NARROW>
+// NARROW != 0: one 2 KB staging box per epilogue warp so that the shared memory saved holds a FIFTH pipeline stage (the k-block
+// period is (load latency + MMA time of a stage) / STAGES, tools/gemm_bound.py).  1 = bf16 output, no row sums (no tile of
+// ones either); 2 = fp32 output (wgrad / split-K partials) stored as 16-column half boxes, row sums kept, 8 epilogue warps.
+template <int BN, int STAGES, int EPI_WARPS, bool AUX, int NARROW>
 __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                              const __grid_constant__ CUtensorMap tma_b,
                                                              const __grid_constant__ CUtensorMap tma_c,
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t RS_COLS = 16;                                        // row-sum accumulator: one N = 16 MMA per k-step
   constexpr uint32_t TMEM_COLS = (ACC_STAGES * (BN + RS_COLS) <= 256) ? 256 : 512;   // power of two >= 2 accumulator stages
-  constexpr uint32_t ONES_BYTES = (AUX || NARROW) ? 0 : 2048;                         // 16 rows x 128 B of bf16 1.0 (the "B operand" of the row sum)
+  constexpr uint32_t ONES_BYTES = (AUX || NARROW == 1) ? 0 : 2048;                         // 16 rows x 128 B of bf16 1.0 (the "B operand" of the row sum)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // per epilogue warp: C boxes (AUX kernels write bf16 only: one 2 KB box per chunk; otherwise 4 KB so that the single
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
   const int total_kb = (p.K + BK - 1) / BK;
   const int n_items = p.tiles_m * p.tiles_n * p.splits;
 
-  if (!AUX && !NARROW && p.rowsum != nullptr) {
+  if (!AUX && NARROW != 1 && p.rowsum != nullptr) {
     for (int i = threadIdx.x; i < (int)(ONES_BYTES / 4); i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA's async proxy
   }
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
           const uint64_t ad0 = make_smem_desc(sa, a_lbo, 1024), bd0 = make_smem_desc(sb, b_lbo, 1024);
           const uint32_t acc_first = kb > kb0 ? 1u : 0u;
           // two straight-line versions of the k-steps (no conditionally executed tensor-core instruction)
-          const bool with_rs = !AUX && !NARROW && p.rowsum != nullptr && (kb % p.tiles_n) == tn;
+          const bool with_rs = !AUX && NARROW != 1 && p.rowsum != nullptr && (kb % p.tiles_n) == tn;
           if (leader) {
             if (p.dbg & 2) {
             } else if (with_rs) {
@@ -344,11 +345,32 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) gemm_tc_kernel(const _
             *reinterpret_cast<uint4*>(stg64(sx, lane, ch)) = pk;
           }
         }
-        const bool single_box = p.out_f32 || NARROW;
+        const bool single_box = p.out_f32 || NARROW != 0;
         uint8_t* sc = dgelu ? sx : (single_box ? stgC : stgC + c * 2048);
         if (single_box && c > 0) {                  // the single box is reused: wait until the previous store has read it
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
+        }
+        if (NARROW == 2) {
+          // fp32 through the 2 KB box: two 16-column halves (32 rows x 64 B, 64B swizzle), one TMA store each
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            if (hb > 0) {
+              if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              __syncwarp();
+            }
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+              *reinterpret_cast<float4*>(stg64(sc, lane, ch)) =
+                  make_float4(v[hb * 16 + ch * 4], v[hb * 16 + ch * 4 + 1], v[hb * 16 + ch * 4 + 2], v[hb * 16 + ch * 4 + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && !(p.dbg & 4) && cb + hb * 16 < p.N) {
+              tma_store_3d(&tma_c, sc, cb + hb * 16, rb, z);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          continue;
         }
         if (p.out_f32) {
 #pragma unroll
@@ -390,10 +412,10 @@ int pick_bn(int N) {
   return (ceil_div(N, 192) * 192 <= ceil_div(N, 128) * 128) ? 192 : 128;
 }
 
-template <int BN, int STAGES, int EPI_WARPS, bool AUX, bool NARROW = false>
+template <int BN, int STAGES, int EPI_WARPS, bool AUX, int NARROW = 0>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, const CUtensorMap& mx, TcParams p, int splits,
            cudaStream_t st) {
-  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + ((AUX || NARROW) ? 0 : 2048) +
+  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + ((AUX || NARROW == 1) ? 0 : 2048) +
                           EPI_WARPS * (AUX ? 2 * ((BN / 32) / (EPI_WARPS / 4)) * 2048 : (NARROW ? 2048 : 4096)) + 1024 + 512;
   static_assert(smem <= 227 * 1024, "gemm_tc: shared memory budget");
   static bool attr_set = false;
@@ -461,7 +483,10 @@ int apb_gemm_tc_rowsum(const void* A, const void* B, void* C, const float* bias,
   APB_CHECK_ARG(N % 8 == 0, APB_ERR_UNSUPPORTED, "gemm_tc: N=%d must be a multiple of 8 (TMA store pitch)", N);
   APB_CHECK_ARG(aux == nullptr || ((uintptr_t)aux & 15) == 0, APB_ERR_ARG, "gemm_tc: aux must be 16-byte aligned");
   CUtensorMap mc, mx;
-  rc = make_map_out(&mc, C, p.out_f32 != 0, M, N, splits);
+  const bool aux_epi0 = (p.epilogue == 1 || p.epilogue == 2);
+  const bool narrow_ok = !(getenv("APB_GEMM_NARROW") && getenv("APB_GEMM_NARROW")[0] == '0');     // A/B switch for tools
+  const bool narrow32 = BN == 192 && !aux_epi0 && p.out_f32 && narrow_ok;
+  rc = make_map_out(&mc, C, p.out_f32 != 0, M, N, splits, narrow32);
   if (rc) return rc;
   const bool aux_map = (epilogue == 1 || epilogue == 2);      // GELU stores gelu' through it, dGELU loads gelu' through it
   rc = make_map_out(&mx, aux_map ? aux : C, aux_map ? false : (p.out_f32 != 0), M, N, aux_map ? 1 : splits);
@@ -471,8 +496,10 @@ int apb_gemm_tc_rowsum(const void* A, const void* B, void* C, const float* bias,
   if (BN == 64) return aux_epi ? launch<64, 6, 8, true>(ma, mb, mc, mx, p, splits, st) : launch<64, 6, 8, false>(ma, mb, mc, mx, p, splits, st);
   // (24 epilogue warps for the GELU kernels were measured on the same box: 19.83 vs 19.79 ms / step with 12 -> kept 12)
   // bf16 output without row sums (forward and dgrad products): 5 stages (APB_GEMM_NARROW=0: the 4-stage kernel, for A/B runs)
-  if (BN == 192 && !aux_epi && !p.out_f32 && rowsum_parts == nullptr && splits == 1 && !(getenv("APB_GEMM_NARROW") && getenv("APB_GEMM_NARROW")[0] == '0'))
-    return launch<192, 5, 12, false, true>(ma, mb, mc, mx, p, splits, st);
+  if (BN == 192 && !aux_epi && !p.out_f32 && rowsum_parts == nullptr && splits == 1 && narrow_ok)
+    return launch<192, 5, 12, false, 1>(ma, mb, mc, mx, p, splits, st);
+  // fp32 output (wgrad, split-K partials): 5 stages, 8 epilogue warps, half-box stores
+  if (narrow32) return launch<192, 5, 8, false, 2>(ma, mb, mc, mx, p, splits, st);
   if (BN == 192) return aux_epi ? launch<192, 3, 12, true>(ma, mb, mc, mx, p, splits, st) : launch<192, 4, 12, false>(ma, mb, mc, mx, p, splits, st);
   return aux_epi ? launch<128, 4, 16, true>(ma, mb, mc, mx, p, splits, st) : launch<128, 4, 16, false>(ma, mb, mc, mx, p, splits, st);
 }

@@ -169,16 +169,17 @@ int make_map(CUtensorMap* map, const void* base, long long rows, long long cols,
 }
 
 // output tensor [splits, M, N] row-major; box {32 columns, 32 rows, 1}: fp32 -> 128 B rows / 128B swizzle, bf16 -> 64 B / 64B
-int make_map_out(CUtensorMap* map, const void* base, bool f32, long long M, long long N, long long splits) {
+// half_box (fp32 only): 16-column boxes (32 rows x 64 B, 64B swizzle) -- the 2 KB staging box of the 5-stage kernels
+int make_map_out(CUtensorMap* map, const void* base, bool f32, long long M, long long N, long long splits, bool half_box = false) {
   EncodeTiledFn enc = get_encode();
   if (enc == nullptr) { apb_set_error("gemm_tc: cuTensorMapEncodeTiled entry point unavailable"); return APB_ERR_UNSUPPORTED; }
   const cuuint64_t esz = f32 ? 4 : 2;
   cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)splits};
   cuuint64_t strides[2] = {(cuuint64_t)N * esz, (cuuint64_t)N * (cuuint64_t)M * esz};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t box[3] = {(cuuint32_t)((f32 && half_box) ? 16 : 32), 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
-                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, (f32 && !half_box) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     apb_set_error("gemm_tc: cuTensorMapEncodeTiled(out) failed (%d) M=%lld N=%lld splits=%lld base=%p", (int)r, M, N, splits, base);
