@@ -72,7 +72,7 @@ SIGNATURES = {
     'apb_gelu_bwd': (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
     'apb_bn_workspace_floats': (_ll, [_ll, _i]),
     'apb_bn_relu_fwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _vp, _ll, _i, _i, _vp]),
-    'apb_bn_relu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
+    'apb_bn_relu_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     'apb_adamw_ema': (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _f, _f, _f, _f, C.POINTER(_vp), C.POINTER(_f), _i, _vp, _vp]),
     'apb_launch_count': (_ll, []),
     'apb_fallback_count': (_ll, []),

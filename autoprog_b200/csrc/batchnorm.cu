@@ -33,21 +33,34 @@ __device__ __forceinline__ void st8(bf16* p, const float (&v)[8]) {
 }
 
 // Column partial sums of two quantities.  MODE 0: (x, x^2).  MODE 1 (backward): g = dy * (y > 0); (g, g * xhat).
+// The ReLU mask is recomputed from x with the forward's own expression (fma(x, a, b) > 0, a = invstd * gamma,
+// b = beta - mean * a) when beta is given, which saves the read of y (a third of the backward's traffic); y is read
+// only when beta == nullptr.
 // block = 256 threads: lane -> 8 consecutive channels, (C/8) lanes cover a row, the rest of the block strides rows.
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) bn_colstats_kernel(const T* __restrict__ x, const T* __restrict__ y,
                                                           const T* __restrict__ dy, const float* __restrict__ mean,
-                                                          const float* __restrict__ invstd, long long rows, int C,
+                                                          const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, long long rows, int C,
                                                           float* __restrict__ part, int rows_per_cta) {
   extern __shared__ float sm[];          // [groups][2][C]
   const int lanes_per_row = C >> 3;
   const int groups = 256 / lanes_per_row;                 // row slots per sweep
   const int slot = threadIdx.x / lanes_per_row, c0 = (threadIdx.x % lanes_per_row) * 8;
   const bool active = slot < groups;
-  float a0[8], a1[8], mu[8], is[8];
+  float a0[8], a1[8], mu[8], is[8], ma[8], mb[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; mu[j] = 0.f; is[j] = 0.f; }
-  if (MODE == 1 && active) { ld8(mean + c0, mu); ld8(invstd + c0, is); }
+  for (int j = 0; j < 8; ++j) { a0[j] = 0.f; a1[j] = 0.f; mu[j] = 0.f; is[j] = 0.f; ma[j] = 0.f; mb[j] = 0.f; }
+  const bool remask = MODE == 1 && beta != nullptr;
+  if (MODE == 1 && active) {
+    ld8(mean + c0, mu); ld8(invstd + c0, is);
+    if (remask) {
+      float ga[8], be[8];
+      ld8(gamma + c0, ga); ld8(beta + c0, be);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ma[j] = is[j] * ga[j]; mb[j] = be[j] - mu[j] * ma[j]; }
+    }
+  }
   const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + (long long)rows_per_cta);
   if (active) {
     // UNR rows in flight per thread (all loads issued before the first use): the kernel is a pure HBM stream
@@ -59,7 +72,10 @@ __global__ void __launch_bounds__(256) bn_colstats_kernel(const T* __restrict__ 
       for (int u = 0; u < UNR; ++u) {
         const size_t o = (size_t)(r + (long long)u * groups) * C + c0;
         ld8(x + o, xv[u]);
-        if (MODE == 1) { ld8(y + o, yv[u]); ld8(dy + o, gv[u]); }
+        if (MODE == 1) {
+          ld8(dy + o, gv[u]);
+          if (!remask) ld8(y + o, yv[u]);
+        }
       }
 #pragma unroll
       for (int u = 0; u < UNR; ++u)
@@ -69,7 +85,8 @@ __global__ void __launch_bounds__(256) bn_colstats_kernel(const T* __restrict__ 
             a0[j] += xv[u][j];
             a1[j] = fmaf(xv[u][j], xv[u][j], a1[j]);
           } else {
-            const float g = yv[u][j] > 0.f ? gv[u][j] : 0.f;
+            const float act = remask ? fmaf(xv[u][j], ma[j], mb[j]) : yv[u][j];
+            const float g = act > 0.f ? gv[u][j] : 0.f;
             a0[j] += g;
             a1[j] = fmaf(g, (xv[u][j] - mu[j]) * is[j], a1[j]);
           }
@@ -83,11 +100,12 @@ __global__ void __launch_bounds__(256) bn_colstats_kernel(const T* __restrict__ 
         for (int j = 0; j < 8; ++j) { a0[j] += xv[j]; a1[j] = fmaf(xv[j], xv[j], a1[j]); }
       } else {
         float yv[8], gv[8];
-        ld8(y + (size_t)r * C + c0, yv);
+        if (!remask) ld8(y + (size_t)r * C + c0, yv);
         ld8(dy + (size_t)r * C + c0, gv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float g = yv[j] > 0.f ? gv[j] : 0.f;
+          const float act = remask ? fmaf(xv[j], ma[j], mb[j]) : yv[j];
+          const float g = act > 0.f ? gv[j] : 0.f;
           a0[j] += g;
           a1[j] = fmaf(g, (xv[j] - mu[j]) * is[j], a1[j]);
         }
@@ -186,6 +204,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
                                                            const T* __restrict__ dy, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd,
                                                            const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta,
                                                            const float* __restrict__ dgamma,
                                                            const float* __restrict__ dbeta, T* __restrict__ dx,
                                                            long long rows, int C) {
@@ -195,23 +214,34 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
   const float inv_n = 1.f / (float)rows;
   const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = (int)(i0 % (C >> 3)) * 8;
-  float k1[8], k2[8], k3[8];
+  float k1[8], k2[8], k3[8], mb[8];
+  const bool remask = beta != nullptr;           // ReLU mask from x (the forward's fma) instead of a read of y
   {
     float mu[8], is[8], ga[8], dg[8], db[8];
     ld8(mean + c0, mu); ld8(invstd + c0, is); ld8(gamma + c0, ga); ld8(dgamma + c0, dg); ld8(dbeta + c0, db);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      k1[j] = ga[j] * is[j];
+      k1[j] = ga[j] * is[j];                     // == the forward's scale a = invstd * gamma
       k2[j] = k1[j] * is[j] * dg[j] * inv_n;
       k3[j] = k2[j] * mu[j] - k1[j] * db[j] * inv_n;
+      mb[j] = 0.f;
+    }
+    if (remask) {
+      float be[8];
+      ld8(beta + c0, be);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mb[j] = be[j] - mu[j] * (is[j] * ga[j]);
     }
   }
-  for (long long i = i0; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = i0; i < nvec; i += step) {
     float xv[8], yv[8], gv[8];
-    ld8(x + i * 8, xv); ld8(y + i * 8, yv); ld8(dy + i * 8, gv);
+    ld8(x + i * 8, xv); ld8(dy + i * 8, gv);
+    if (!remask) ld8(y + i * 8, yv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float g = yv[j] > 0.f ? gv[j] : 0.f;
+      const float act = remask ? fmaf(xv[j], k1[j], mb[j]) : yv[j];
+      const float g = act > 0.f ? gv[j] : 0.f;
       xv[j] = fmaf(k1[j], g, fmaf(-k2[j], xv[j], k3[j]));
     }
     st8(dx + i * 8, xv);
@@ -245,10 +275,10 @@ int apb_bn_relu_fwd(const void* x, void* y, const float* gamma, const float* bet
   if (use_batch_stats) {
     if (dtype == APB_F32) {
       cudaFuncSetAttribute(bn_colstats_kernel<float, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      bn_colstats_kernel<float, 0><<<parts, 256, smem, st>>>((const float*)x, nullptr, nullptr, nullptr, nullptr, rows, C, workspace, BN_ROWS_PER_CTA);
+      bn_colstats_kernel<float, 0><<<parts, 256, smem, st>>>((const float*)x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rows, C, workspace, BN_ROWS_PER_CTA);
     } else {
       cudaFuncSetAttribute(bn_colstats_kernel<bf16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      bn_colstats_kernel<bf16, 0><<<parts, 256, smem, st>>>((const bf16*)x, nullptr, nullptr, nullptr, nullptr, rows, C, workspace, BN_ROWS_PER_CTA);
+      bn_colstats_kernel<bf16, 0><<<parts, 256, smem, st>>>((const bf16*)x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, rows, C, workspace, BN_ROWS_PER_CTA);
     }
     APB_LAUNCH_CHECK("bn_colstats");
     bn_finalize_fwd_kernel<<<ceil_div(C, 8), 256, 0, st>>>(workspace, parts, C, rows, eps, momentum, mean, invstd, running_mean, running_var);
@@ -261,28 +291,29 @@ int apb_bn_relu_fwd(const void* x, void* y, const float* gamma, const float* bet
   return 0;
 }
 
-int apb_bn_relu_bwd(const void* x, const void* y, const void* dy, const float* gamma, const float* mean, const float* invstd,
-                    void* dx, float* dgamma, float* dbeta, float* workspace, long long rows, int C, int dtype,
+int apb_bn_relu_bwd(const void* x, const void* y, const void* dy, const float* gamma, const float* beta, const float* mean,
+                    const float* invstd, void* dx, float* dgamma, float* dbeta, float* workspace, long long rows, int C, int dtype,
                     apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
   APB_CHECK_ARG(rows > 0 && C > 0 && (C % 8) == 0 && C <= 2048 && 256 % (C / 8) == 0, APB_ERR_SHAPE, "bn_relu_bwd: rows=%lld C=%d", rows, C);
   APB_CHECK_ARG(dtype == APB_F32 || dtype == APB_BF16, APB_ERR_DTYPE, "bn_relu_bwd: dtype %d", dtype);
+  APB_CHECK_ARG(y != nullptr || beta != nullptr, APB_ERR_ARG, "bn_relu_bwd: needs y or beta for the ReLU mask");
   const int parts = bn_parts(rows);
   const int groups = 256 / (C / 8);
   const size_t smem = (size_t)groups * 2 * C * sizeof(float);
   const long long nvec = rows * (C / 8);
   if (dtype == APB_F32) {
     cudaFuncSetAttribute(bn_colstats_kernel<float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    bn_colstats_kernel<float, 1><<<parts, 256, smem, st>>>((const float*)x, (const float*)y, (const float*)dy, mean, invstd, rows, C, workspace, BN_ROWS_PER_CTA);
+    bn_colstats_kernel<float, 1><<<parts, 256, smem, st>>>((const float*)x, (const float*)y, (const float*)dy, mean, invstd, gamma, beta, rows, C, workspace, BN_ROWS_PER_CTA);
     APB_LAUNCH_CHECK("bn_colstats_bwd");
     bn_finalize_bwd_kernel<<<ceil_div(C, 8), 256, 0, st>>>(workspace, parts, C, dgamma, dbeta);
-    bn_bwd_apply_kernel<float><<<bn_grid(nvec), 256, 0, st>>>((const float*)x, (const float*)y, (const float*)dy, mean, invstd, gamma, dgamma, dbeta, (float*)dx, rows, C);
+    bn_bwd_apply_kernel<float><<<bn_grid(nvec), 256, 0, st>>>((const float*)x, (const float*)y, (const float*)dy, mean, invstd, gamma, beta, dgamma, dbeta, (float*)dx, rows, C);
   } else {
     cudaFuncSetAttribute(bn_colstats_kernel<bf16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    bn_colstats_kernel<bf16, 1><<<parts, 256, smem, st>>>((const bf16*)x, (const bf16*)y, (const bf16*)dy, mean, invstd, rows, C, workspace, BN_ROWS_PER_CTA);
+    bn_colstats_kernel<bf16, 1><<<parts, 256, smem, st>>>((const bf16*)x, (const bf16*)y, (const bf16*)dy, mean, invstd, gamma, beta, rows, C, workspace, BN_ROWS_PER_CTA);
     APB_LAUNCH_CHECK("bn_colstats_bwd");
     bn_finalize_bwd_kernel<<<ceil_div(C, 8), 256, 0, st>>>(workspace, parts, C, dgamma, dbeta);
-    bn_bwd_apply_kernel<bf16><<<bn_grid(nvec), 256, 0, st>>>((const bf16*)x, (const bf16*)y, (const bf16*)dy, mean, invstd, gamma, dgamma, dbeta, (bf16*)dx, rows, C);
+    bn_bwd_apply_kernel<bf16><<<bn_grid(nvec), 256, 0, st>>>((const bf16*)x, (const bf16*)y, (const bf16*)dy, mean, invstd, gamma, beta, dgamma, dbeta, (bf16*)dx, rows, C);
   }
   APB_LAUNCH_CHECK("bn_bwd_apply");
   return 0;

@@ -399,15 +399,16 @@ def bn_relu_fwd(x, gamma, beta, running_mean, running_var, momentum: float, eps:
     return y, mean, invstd
 
 
-def bn_relu_bwd(x, y, dy, gamma, mean, invstd):
+def bn_relu_bwd(x, y, dy, gamma, mean, invstd, beta=None):
+    """beta given: the ReLU mask is recomputed from x (y may be None and is not read); else it is read from y."""
     Cc = x.shape[-1]
     rows = x.numel() // Cc
     dx = torch.empty_like(x)
     dg = torch.empty(Cc, device=x.device, dtype=torch.float32)
     db = torch.empty(Cc, device=x.device, dtype=torch.float32)
     ws = torch.empty(int(lib().apb_bn_workspace_floats(rows, Cc)), device=x.device, dtype=torch.float32)
-    check(lib().apb_bn_relu_bwd(_p(x), _p(y), _p(dy), _p(gamma), _p(mean), _p(invstd), _p(dx), _p(dg), _p(db), _p(ws), rows, Cc,
-                                dt(x), _st()), 'bn_relu_bwd')
+    check(lib().apb_bn_relu_bwd(_p(x), _p(y), _p(dy), _p(gamma), _p(beta), _p(mean), _p(invstd), _p(dx), _p(dg), _p(db), _p(ws),
+                                rows, Cc, dt(x), _st()), 'bn_relu_bwd')
     return dx, dg, db
 
 

@@ -488,16 +488,17 @@ class BNReLUFn(torch.autograd.Function):
         xc = _c(x)
         y, mean, invstd = K.bn_relu_fwd(xc, weight.detach().float(), bias.detach().float(), running_mean, running_var,
                                         momentum, eps, training)
-        ctx.save_for_backward(xc, y, weight.detach().float(), mean, invstd)
+        # backward recomputes the ReLU mask from x (kernel reads x and dy only): y is not kept for it
+        ctx.save_for_backward(xc, weight.detach().float(), bias.detach().float(), mean, invstd)
         ctx.training = training
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        xc, y, w, mean, invstd = ctx.saved_tensors
+        xc, w, b, mean, invstd = ctx.saved_tensors
         if not ctx.training:
             raise RuntimeError('BNReLUFn: backward through eval-mode BatchNorm is not supported')
-        dx, dg, db = K.bn_relu_bwd(xc, y, K.cast(_c(dy), xc.dtype), w, mean, invstd)
+        dx, dg, db = K.bn_relu_bwd(xc, None, K.cast(_c(dy), xc.dtype), w, mean, invstd, beta=b)
         return dx, dg, db, None, None, None, None, None
 
 

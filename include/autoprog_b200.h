@@ -224,7 +224,9 @@ long long apb_bn_workspace_floats(long long rows, int C);
 int apb_bn_relu_fwd(const void* x, void* y, const float* gamma, const float* beta, float* mean, float* invstd,
                     float* running_mean, float* running_var, float momentum, float eps, int use_batch_stats,
                     float* workspace, long long rows, int C, int dtype, apb_stream_t stream);
-int apb_bn_relu_bwd(const void* x, const void* y, const void* dy, const float* gamma, const float* mean,
+/* backward: the ReLU mask is recomputed from x with the forward's expression when beta is given (y may then be NULL and is
+ * not read: a third less traffic); with beta == NULL the mask is read from y. */
+int apb_bn_relu_bwd(const void* x, const void* y, const void* dy, const float* gamma, const float* beta, const float* mean,
                     const float* invstd, void* dx, float* dgamma, float* dbeta, float* workspace, long long rows, int C,
                     int dtype, apb_stream_t stream);
 

@@ -475,10 +475,12 @@ def test_batchnorm_relu_fused(rows, C, dtype):
     t = tol(dtype)
     assert rel(y, yr) < t
     assert rel(rmd, bn.running_mean) < 1e-5 and rel(rvd, bn.running_var) < 1e-5
-    # backward uses the mask of the STORED output, so feed the oracle's mask through the same rounding
+    # two mask sources: the STORED output y, and (what the model uses) the forward's expression recomputed from x
     dx, dg, db = K.bn_relu_bwd(x.to(dev, dtype), y, dy.to(dev, dtype), g.to(dev), mean, invstd)
     assert rel(dx, xr.grad) < (t if dtype == torch.float32 else 3e-2), rel(dx, xr.grad)
     assert rel(dg, bn.weight.grad) < max(t, 1e-4) and rel(db, bn.bias.grad) < max(t, 1e-4)
+    dx2, dg2, db2 = K.bn_relu_bwd(x.to(dev, dtype), None, dy.to(dev, dtype), g.to(dev), mean, invstd, beta=b.to(dev))
+    assert torch.equal(dx2, dx) and torch.equal(dg2, dg) and torch.equal(db2, db)      # same mask -> bit-identical
     bn.eval()
     ye, _, _ = K.bn_relu_fwd(x.to(dev, dtype), g.to(dev), b.to(dev), rmd, rvd, 0.1, 1e-5, False)
     assert rel(ye, torch.relu(bn(x))) < t
