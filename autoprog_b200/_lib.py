@@ -78,6 +78,7 @@ SIGNATURES = {
     'apb_fallback_count': (_ll, []),
     'apb_set_pdl': (None, [_i]),
     'apb_get_pdl': (_i, []),
+    'apb_debug_gemm_switches': (None, [_i, _i]),
     'apb_debug_umma_probe': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     'apb_debug_umma_timing': (_i, [_vp, _i, _i, _i, _vp]),
     'apb_debug_mhsa_trace': (_i, [_vp]),

@@ -42,8 +42,8 @@ typedef __nv_bfloat16 bf16;
 // its predecessor in the stream is still draining; it must execute pdl_wait() BEFORE its first global-memory access (the
 // wait returns once every prerequisite grid has completed and its writes are visible).  pdl_trigger() lets the NEXT
 // kernel in the stream start its own prologue; it is placed after the wait, so at most two grids are in flight.
-// Both instructions are no-ops for a kernel launched without the attribute.  g_apb_pdl: APB_PDL=0 disables the attribute.
-extern int g_apb_pdl;
+// Both instructions are no-ops for a kernel launched without the attribute.  g_apb_pdl (apb_set_pdl): off by default.
+extern int g_apb_pdl, g_apb_gemm_dbg, g_apb_gemm_narrow;
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <typename... KArgs, typename... Args>

@@ -23,7 +23,6 @@
 //   * rowsum (apb_gemm_tc_rowsum): sum_k A(m,k) -- the bias gradient of a wgrad GEMM -- from one extra 128 x 16 x 16 MMA
 //     per k-step against a tile of ones, shared between the n-tiles of an m-tile.
 // The forward-shaped K >= 384 products run on CTA pairs instead (gemm_tc2.cu, cta_group::2).
-#include <stdlib.h>
 #include "gemm_tc_common.cuh"
 
 namespace {
@@ -43,7 +42,7 @@ struct TcParams {
   int kb_per_split;     // k-blocks per split
   int splits;
   int tiles_m, tiles_n;
-  int dbg;              // diagnostics (APB_GEMM_DBG, tools/gemm_bound.py): 1 = no TMA loads (stale operands), 2 = no MMAs, 4 = no stores
+  int dbg;              // diagnostics (apb_debug_gemm_switches, tools/gemm_bound.py): 1 = no TMA loads (stale operands), 2 = no MMAs, 4 = no stores
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -427,10 +426,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mc, 
   p.tiles_m = ceil_div(p.M, BM);
   p.tiles_n = ceil_div(p.N, BN);
   p.splits = splits;
-  {
-    const char* e = getenv("APB_GEMM_DBG");
-    p.dbg = e ? atoi(e) : 0;
-  }
+  p.dbg = g_apb_gemm_dbg;
   const long long items = (long long)p.tiles_m * p.tiles_n * splits;
   const int grid = (int)(items < num_sms() ? items : num_sms());
   apb_launch_pdl(gemm_tc_kernel<BN, STAGES, EPI_WARPS, AUX, NARROW>, dim3(grid), dim3(64 + EPI_WARPS * 32), smem, st, ma, mb, mc, mx, p);
@@ -484,7 +480,7 @@ int apb_gemm_tc_rowsum(const void* A, const void* B, void* C, const float* bias,
   APB_CHECK_ARG(aux == nullptr || ((uintptr_t)aux & 15) == 0, APB_ERR_ARG, "gemm_tc: aux must be 16-byte aligned");
   CUtensorMap mc, mx;
   const bool aux_epi0 = (p.epilogue == 1 || p.epilogue == 2);
-  const bool narrow_ok = !(getenv("APB_GEMM_NARROW") && getenv("APB_GEMM_NARROW")[0] == '0');     // A/B switch for tools
+  const bool narrow_ok = g_apb_gemm_narrow != 0;     // A/B switch for tools (apb_debug_gemm_switches)
   const bool narrow32 = BN == 192 && !aux_epi0 && p.out_f32 && narrow_ok;
   rc = make_map_out(&mc, C, p.out_f32 != 0, M, N, splits, narrow32);
   if (rc) return rc;
@@ -495,7 +491,7 @@ int apb_gemm_tc_rowsum(const void* A, const void* B, void* C, const float* bias,
   APB_CHECK_ARG(!(aux_epi && rowsum_parts != nullptr), APB_ERR_UNSUPPORTED, "gemm_tc: row sums are not available with GELU epilogues");
   if (BN == 64) return aux_epi ? launch<64, 6, 8, true>(ma, mb, mc, mx, p, splits, st) : launch<64, 6, 8, false>(ma, mb, mc, mx, p, splits, st);
   // (24 epilogue warps for the GELU kernels were measured on the same box: 19.83 vs 19.79 ms / step with 12 -> kept 12)
-  // bf16 output without row sums (forward and dgrad products): 5 stages (APB_GEMM_NARROW=0: the 4-stage kernel, for A/B runs)
+  // bf16 output without row sums (forward and dgrad products): 5 stages
   if (BN == 192 && !aux_epi && !p.out_f32 && rowsum_parts == nullptr && splits == 1 && narrow_ok)
     return launch<192, 5, 12, false, 1>(ma, mb, mc, mx, p, splits, st);
   // fp32 output (wgrad, split-K partials): 5 stages, 8 epilogue warps, half-box stores

@@ -436,6 +436,12 @@ def get_pdl() -> bool:
     return bool(lib().apb_get_pdl())
 
 
+def debug_gemm_switches(dbg: int = 0, five_stage: bool = True) -> None:
+    """Diagnostics for tools/gemm_bound.py: bit 0 no TMA loads, bit 1 no MMAs, bit 2 no stores; five_stage=False times the
+    four-stage 128 x 192 kernels."""
+    lib().apb_debug_gemm_switches(int(dbg), int(bool(five_stage)))
+
+
 def fallback_count() -> int:
     """bf16 calls that a tensor-core kernel declined and a CUDA-core kernel served (each one is also logged on stderr)."""
     return int(lib().apb_fallback_count())

@@ -11,8 +11,9 @@
  *   - dtype codes: APB_F32 = 0, APB_BF16 = 1 (activations); parameters / statistics / loss are fp32;
  *   - return value: 0 = ok, > 0 = cudaError_t of the failed launch, < 0 = argument check
  *     (-1 arg, -2 dtype, -3 shape, -4 unsupported); `apb_last_error()` has the message (thread-local);
- *   - thread-safe: no mutable global state except a mutex-guarded TMA-descriptor cache; all work is
- *     enqueued on the given stream (CUDA-graph capturable).
+ *   - thread-safe: no mutable global state except a mutex-guarded TMA-descriptor cache, the launch / fallback evidence
+ *     counters and the diagnostic switches at the end of this header (plain ints, set only by tools, never read from
+ *     the environment); all work is enqueued on the given stream (CUDA-graph capturable).
  */
 #ifndef AUTOPROG_B200_H_
 #define AUTOPROG_B200_H_
@@ -248,9 +249,12 @@ long long apb_fallback_count(void);
 /* programmatic dependent launch: the hot kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization so
  * that their prologue overlaps the previous kernel's tail (each one executes griddepcontrol.wait before its first
  * global-memory access).  Off by default (saves 0.7-1.6 us per launch in chains of one kernel, neutral on the whole
- * training step); APB_PDL=1 in the environment or apb_set_pdl(1) turns it on. */
+ * training step); apb_set_pdl(1) turns it on. */
 void apb_set_pdl(int on);
 int apb_get_pdl(void);
+/* diagnostic (tools/gemm_bound.py): dbg bit 0 = no TMA loads, bit 1 = no MMAs, bit 2 = no stores in the tcgen05 GEMM;
+ * five_stage = 0 selects the four-stage 128x192 kernels for A/B timing.  Defaults: (0, 1). */
+void apb_debug_gemm_switches(int dbg, int five_stage);
 
 /* diagnostic (tools/umma_probe.py): D[128,32] = A[128,64] * B[64, off:off+32] through ONE descriptor convention
  * (mode 0..3, see csrc/umma_probe.cu); pins the shared-memory layouts the attention kernels rely on. */
