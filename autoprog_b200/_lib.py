@@ -25,7 +25,7 @@ SIGNATURES = {
     'apb_outlook_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     'apb_outlook_bwd': (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _i, _vp]),
     'apb_tlce_workspace_floats': (_ll, [_i, _i]),
-    'apb_tlce_fwd_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _f, _f, _vp, _vp, _vp, _vp, _i, _vp]),
+    'apb_tlce_fwd_bwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     'apb_token_label_target': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _i, _vp]),
     'apb_onehot_smooth': (_i, [_vp, _vp, _i, _i, _f, _vp]),
     'apb_scale_lazy': (_i, [_vp, _ll, _vp, _ll, _vp, _vp, _i, _vp]),

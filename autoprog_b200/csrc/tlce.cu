@@ -30,6 +30,11 @@ struct TlceParams {
   float w_cls, w_dense;        // already divided by B and B*N
   int tiles_per_img;
   int cta_offset;              // added to blockIdx.x (the fast path launches only the class-token CTAs of tlce_kernel)
+  // single-launch fast path (ticket != nullptr): CTAs [0, B) class tokens, [B, B + n_aux) dense tiles; the LAST CTA
+  // to finish (ticket counter) sums all partials in the fixed order of tlce_reduce_kernel, writes the loss, re-arms the ticket
+  int* ticket;
+  float* loss;
+  int n_aux;
 };
 
 template <typename T>
@@ -140,6 +145,100 @@ __global__ void __launch_bounds__(NTHREADS) tlce_kernel(TlceParams p) {
   }
 }
 
+// Class-token part of the fast path: one CTA per image, thread = classes tid, tid + 256, ...  The class-level labels sit
+// at stride (2 + N) floats in the class-major target, i.e. every load is its own sector: all of a thread's loads (own image
+// and, when mixing, the flipped image) are issued before the first use and kept in registers for the gradient pass -- the
+// warp-per-image loop this replaces walked 2 x 32 dependent strided loads per lane (32 us for 128 images).
+constexpr int CLS_MAXJ = 4;            // classes per thread (C <= 1024)
+template <typename T>
+__device__ __forceinline__ void tlce_cls_body(const TlceParams& p, int b, int partial_index) {
+  __shared__ float red[3][NTHREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.C;
+  const T* xr = reinterpret_cast<const T*>(p.x_cls) + (size_t)b * C;
+  T* dr = reinterpret_cast<T*>(p.d_cls) + (size_t)b * C;
+  const float* t0 = p.target + (size_t)b * p.t_sb + (size_t)p.slot_cls * p.t_ss;
+  const float* t1 = p.target + (size_t)(p.B - 1 - b) * p.t_sb + (size_t)p.slot_cls * p.t_ss;
+  float lam = p.lam;
+  if (p.box_dev != nullptr) lam = 1.f - (float)((p.box_dev[2] - p.box_dev[0]) * (p.box_dev[3] - p.box_dev[1])) / (float)p.N;
+  const bool mix = lam < 1.f;
+  float x[CLS_MAXJ], t[CLS_MAXJ], u[CLS_MAXJ];
+#pragma unroll
+  for (int j = 0; j < CLS_MAXJ; ++j) {
+    const int c = tid + j * NTHREADS;
+    const bool ok = c < C;
+    x[j] = ok ? to_f(xr[c]) : -INFINITY;
+    t[j] = ok ? t0[(size_t)c * p.t_sc] : 0.f;
+    u[j] = (ok && mix) ? t1[(size_t)c * p.t_sc] : 0.f;
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < CLS_MAXJ; ++j) {
+    if (mix) t[j] = lam * t[j] + (1.f - lam) * u[j];
+    m = fmaxf(m, x[j]);
+  }
+  m = warp_max(m);
+  if (lane == 0) red[0][warp] = m;
+  __syncthreads();
+  m = red[0][0];
+#pragma unroll
+  for (int i = 1; i < NTHREADS / 32; ++i) m = fmaxf(m, red[0][i]);
+  __syncthreads();
+  float se = 0.f, sum_t = 0.f, sum_tx = 0.f;
+#pragma unroll
+  for (int j = 0; j < CLS_MAXJ; ++j)
+    if (tid + j * NTHREADS < C) {
+      se += expf(x[j] - m);
+      sum_t += t[j];
+      sum_tx = fmaf(t[j], x[j], sum_tx);
+    }
+  se = warp_sum(se); sum_t = warp_sum(sum_t); sum_tx = warp_sum(sum_tx);
+  if (lane == 0) { red[0][warp] = se; red[1][warp] = sum_t; red[2][warp] = sum_tx; }
+  __syncthreads();
+  se = sum_t = sum_tx = 0.f;
+#pragma unroll
+  for (int i = 0; i < NTHREADS / 32; ++i) { se += red[0][i]; sum_t += red[1][i]; sum_tx += red[2][i]; }     // fixed order
+  const float lse = m + logf(se);
+#pragma unroll
+  for (int j = 0; j < CLS_MAXJ; ++j) {
+    const int c = tid + j * NTHREADS;
+    if (c < C) dr[c] = from_f<T>(p.w_cls * (expf(x[j] - lse) * sum_t - t[j]));
+  }
+  if (tid == 0) p.partial[partial_index] = p.w_cls * (lse * sum_t - sum_tx);
+}
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS) tlce_cls_kernel(TlceParams p, int partial_base) {
+  tlce_cls_body<T>(p, blockIdx.x, partial_base + blockIdx.x);
+}
+
+// last-CTA reduction of the per-CTA partials: same order as tlce_reduce_kernel (strided per-thread double sums, then a
+// fixed tree), so the loss does not depend on which CTA happens to finish last
+__device__ __forceinline__ void tlce_ticket_reduce(const TlceParams& p, double* sred) {
+  __shared__ int is_last;
+  const int tid = threadIdx.x;
+  const int total = (int)gridDim.x;
+  if (tid == 0) {
+    __threadfence();                                    // this CTA's partial is visible before the ticket is taken
+    is_last = (atomicAdd(p.ticket, 1) == total - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double acc = 0.0;
+  for (int i = tid; i < total; i += NTHREADS) acc += (double)__ldcg(p.partial + i);
+  sred[tid] = acc;
+  __syncthreads();
+  for (int o = NTHREADS / 2; o > 0; o >>= 1) {
+    if (tid < o) sred[tid] += sred[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) {
+    *p.loss = (float)sred[0];
+    *p.ticket = 0;                                      // re-armed for the next call
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------
 // Fast dense path (3-D class-major target, C a multiple of the 16-byte vector width, C <= 1024: ImageNet's C = 1000).
 // CTA = 16 tokens of one image, 8 warps, 2 tokens per warp:
@@ -166,11 +265,21 @@ __global__ void __launch_bounds__(NTHREADS, 2) tlce_fast_kernel(TlceParams p) {
   __shared__ float s_loss[NTHREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.C, N = p.N;
-  const int b = blockIdx.x / p.tiles_per_img;
-  const int n0 = (blockIdx.x % p.tiles_per_img) * FT;
+  // single-launch mode: the B class-token CTAs come FIRST in the grid (their strided label loads are pure latency: started
+  // early they overlap the dense tiles instead of forming the tail), the dense tiles follow
+  const int cls_ctas = p.ticket != nullptr ? p.B : 0;
+  if ((int)blockIdx.x < cls_ctas) {
+    tlce_cls_body<T>(p, (int)blockIdx.x, (int)blockIdx.x);
+    tlce_ticket_reduce(p, reinterpret_cast<double*>(smem_raw));
+    return;
+  }
+  const int tile = (int)blockIdx.x - cls_ctas;
+  const int b = tile / p.tiles_per_img;
+  const int n0 = (tile % p.tiles_per_img) * FT;
   const int nt = min(FT, N - n0);
-  // ---- (1) this warp's two logit rows -> registers
-  float x[2][NJ * V];
+  // ---- (1) this warp's two logit rows -> registers, still PACKED (bf16: 32 registers instead of 64), so that the staging
+  //      loop below can keep twice as many target loads in flight under the 128-register budget of two CTAs per SM
+  Vec16<T> xraw[2][NJ];
   bool have[2];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
@@ -180,15 +289,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) tlce_fast_kernel(TlceParams p) {
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int c = (lane + 32 * j) * V;
-      if (have[q] && c < C) {
-        Vec16<T> v;
-        v.load(xr + c);
-#pragma unroll
-        for (int k = 0; k < V; ++k) x[q][j * V + k] = v.get(k);
-      } else {
-#pragma unroll
-        for (int k = 0; k < V; ++k) x[q][j * V + k] = -INFINITY;
-      }
+      if (have[q] && c < C) xraw[q][j].load(xr + c);
+      else xraw[q][j].zero();
     }
   }
   // ---- (2) target tile [C, FT] -> shared memory [FT][FCS]
@@ -199,7 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) tlce_fast_kernel(TlceParams p) {
     const bool vec_ok = (((size_t)b * p.t_sb + (size_t)(p.slot_aux0 + n0)) % 2 == 0) && (p.t_sc % 2 == 0);   // 8-byte aligned float2 loads
     // UNR independent class rows per lane in flight: all loads first, then the swizzled stores (the loop is otherwise a
     // chain of dependent load -> store pairs and runs at DRAM latency, not bandwidth)
-    constexpr int UNR = 8;
+    constexpr int UNR = sizeof(T) == 2 ? 16 : 8;
     constexpr int CSTEP = (NTHREADS / 32) * 4;
     for (int cb = warp * 4; cb < C; cb += CSTEP * UNR) {
       float t0[UNR], t1[UNR];
@@ -230,6 +332,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) tlce_fast_kernel(TlceParams p) {
     }
   }
   __syncthreads();
+  float x[2][NJ * V];
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const bool ok = have[q] && (lane + 32 * j) * V < C;
+#pragma unroll
+      for (int k = 0; k < V; ++k) x[q][j * V + k] = ok ? xraw[q][j].get(k) : -INFINITY;
+    }
   // ---- (3) one token per warp pass
   float my_loss = 0.f;
 #pragma unroll
@@ -294,71 +405,13 @@ __global__ void __launch_bounds__(NTHREADS, 2) tlce_fast_kernel(TlceParams p) {
     for (int i = 0; i < NTHREADS / 32; ++i) s += s_loss[i];
     p.partial[blockIdx.x] = s;
   }
+  if (p.ticket != nullptr) {
+    __syncthreads();                                               // every warp is done with the staged tile
+    tlce_ticket_reduce(p, reinterpret_cast<double*>(smem_raw));
+  }
 }
 
 // deterministic final reduction of the per-CTA partials (fixed tree order)
-// Class-token part of the fast path: one CTA per image, thread = classes tid, tid + 256, ...  The class-level labels sit
-// at stride (2 + N) floats in the class-major target, i.e. every load is its own sector: all of a thread's loads (own image
-// and, when mixing, the flipped image) are issued before the first use and kept in registers for the gradient pass -- the
-// warp-per-image loop this replaces walked 2 x 32 dependent strided loads per lane (32 us for 128 images).
-constexpr int CLS_MAXJ = 4;            // classes per thread (C <= 1024)
-template <typename T>
-__global__ void __launch_bounds__(NTHREADS) tlce_cls_kernel(TlceParams p, int partial_base) {
-  __shared__ float red[3][NTHREADS / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x, C = p.C;
-  const T* xr = reinterpret_cast<const T*>(p.x_cls) + (size_t)b * C;
-  T* dr = reinterpret_cast<T*>(p.d_cls) + (size_t)b * C;
-  const float* t0 = p.target + (size_t)b * p.t_sb + (size_t)p.slot_cls * p.t_ss;
-  const float* t1 = p.target + (size_t)(p.B - 1 - b) * p.t_sb + (size_t)p.slot_cls * p.t_ss;
-  float lam = p.lam;
-  if (p.box_dev != nullptr) lam = 1.f - (float)((p.box_dev[2] - p.box_dev[0]) * (p.box_dev[3] - p.box_dev[1])) / (float)p.N;
-  const bool mix = lam < 1.f;
-  float x[CLS_MAXJ], t[CLS_MAXJ], u[CLS_MAXJ];
-#pragma unroll
-  for (int j = 0; j < CLS_MAXJ; ++j) {
-    const int c = tid + j * NTHREADS;
-    const bool ok = c < C;
-    x[j] = ok ? to_f(xr[c]) : -INFINITY;
-    t[j] = ok ? t0[(size_t)c * p.t_sc] : 0.f;
-    u[j] = (ok && mix) ? t1[(size_t)c * p.t_sc] : 0.f;
-  }
-  float m = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < CLS_MAXJ; ++j) {
-    if (mix) t[j] = lam * t[j] + (1.f - lam) * u[j];
-    m = fmaxf(m, x[j]);
-  }
-  m = warp_max(m);
-  if (lane == 0) red[0][warp] = m;
-  __syncthreads();
-  m = red[0][0];
-#pragma unroll
-  for (int i = 1; i < NTHREADS / 32; ++i) m = fmaxf(m, red[0][i]);
-  __syncthreads();
-  float se = 0.f, sum_t = 0.f, sum_tx = 0.f;
-#pragma unroll
-  for (int j = 0; j < CLS_MAXJ; ++j)
-    if (tid + j * NTHREADS < C) {
-      se += expf(x[j] - m);
-      sum_t += t[j];
-      sum_tx = fmaf(t[j], x[j], sum_tx);
-    }
-  se = warp_sum(se); sum_t = warp_sum(sum_t); sum_tx = warp_sum(sum_tx);
-  if (lane == 0) { red[0][warp] = se; red[1][warp] = sum_t; red[2][warp] = sum_tx; }
-  __syncthreads();
-  se = sum_t = sum_tx = 0.f;
-#pragma unroll
-  for (int i = 0; i < NTHREADS / 32; ++i) { se += red[0][i]; sum_t += red[1][i]; sum_tx += red[2][i]; }     // fixed order
-  const float lse = m + logf(se);
-#pragma unroll
-  for (int j = 0; j < CLS_MAXJ; ++j) {
-    const int c = tid + j * NTHREADS;
-    if (c < C) dr[c] = from_f<T>(p.w_cls * (expf(x[j] - lse) * sum_t - t[j]));
-  }
-  if (tid == 0) p.partial[partial_base + b] = p.w_cls * (lse * sum_t - sum_tx);
-}
-
 __global__ void __launch_bounds__(256) tlce_reduce_kernel(const float* __restrict__ partial, int n, float* loss) {
   __shared__ double s[256];
   double acc = 0.0;
@@ -388,7 +441,7 @@ long long apb_tlce_workspace_floats(int B, int N) {
 
 int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, int target_is_3d, int B, int N, int C,
                      int box_area, const int* box_dev, float w_cls, float w_dense, float* loss, void* d_cls, void* d_aux,
-                     float* workspace, int dtype, apb_stream_t stream) {
+                     float* workspace, int* ticket, int dtype, apb_stream_t stream) {
   cudaStream_t st = APB_STREAM(stream);
   APB_CHECK_ARG(B > 0 && N > 0 && C > 0, APB_ERR_SHAPE, "tlce: bad shape B=%d N=%d C=%d", B, N, C);
   APB_CHECK_ARG(dtype == APB_F32 || dtype == APB_BF16, APB_ERR_DTYPE, "tlce: dtype %d", dtype);
@@ -406,6 +459,7 @@ int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, 
   const int grid = B * p.tiles_per_img + n_cls_ctas;
   const size_t esz = dtype == APB_F32 ? 4 : 2;
   p.cta_offset = 0;
+  p.ticket = nullptr; p.loss = loss; p.n_aux = B * p.tiles_per_img;
   cudaError_t e;
   // fast dense path: class-major 3-D target, 16-byte logit rows, C <= 1024
   const int vecw = dtype == APB_F32 ? 4 : 8;
@@ -413,16 +467,19 @@ int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, 
   if (fast) {
     const size_t fsmem = (size_t)FT * FCS * sizeof(float);
     const int n_aux = B * p.tiles_per_img;
+    p.ticket = ticket;                                   // non-null: ONE launch (dense tiles + class tokens + last-CTA reduce)
+    const int fgrid = ticket != nullptr ? n_aux + B : n_aux;
     if (dtype == APB_F32) {
       e = cudaFuncSetAttribute(tlce_fast_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
       if (e != cudaSuccess) { apb_set_error("tlce: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-      tlce_fast_kernel<float><<<n_aux, NTHREADS, fsmem, st>>>(p);
+      tlce_fast_kernel<float><<<fgrid, NTHREADS, fsmem, st>>>(p);
     } else {
       e = cudaFuncSetAttribute(tlce_fast_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
       if (e != cudaSuccess) { apb_set_error("tlce: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-      tlce_fast_kernel<bf16><<<n_aux, NTHREADS, fsmem, st>>>(p);
+      tlce_fast_kernel<bf16><<<fgrid, NTHREADS, fsmem, st>>>(p);
     }
     APB_LAUNCH_CHECK("tlce_fast_kernel");
+    if (ticket != nullptr) return 0;
     if (dtype == APB_F32) tlce_cls_kernel<float><<<B, NTHREADS, 0, st>>>(p, n_aux);
     else tlce_cls_kernel<bf16><<<B, NTHREADS, 0, st>>>(p, n_aux);
     APB_LAUNCH_CHECK("tlce_cls_kernel");

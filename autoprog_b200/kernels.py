@@ -62,7 +62,18 @@ def outlook_bwd(v, logits, dy, heads: int, scale: float, simt: bool = False) -> 
 
 
 # ------------------------------------------------------------------ token-label CE
-def tlce_fwd_bwd(x_cls, x_aux, target, box_area: int, w_cls: float, w_dense: float, box_dev=None):
+_TLCE_TICKETS = {}     # (device index, stream) -> zero int32 ticket of the single-launch loss kernel (re-armed by the kernel)
+
+
+def _tlce_ticket(device: torch.device) -> torch.Tensor:
+    key = (device.index, _st())
+    t = _TLCE_TICKETS.get(key)
+    if t is None:
+        t = _TLCE_TICKETS[key] = torch.zeros(1, device=device, dtype=torch.int32)
+    return t
+
+
+def tlce_fwd_bwd(x_cls, x_aux, target, box_area: int, w_cls: float, w_dense: float, box_dev=None, single_launch: bool = True):
     B, N, Cc = x_aux.shape
     assert x_cls.shape == (B, Cc) and x_cls.dtype == x_aux.dtype
     assert target.dtype == torch.float32
@@ -72,8 +83,9 @@ def tlce_fwd_bwd(x_cls, x_aux, target, box_area: int, w_cls: float, w_dense: flo
     d_cls = torch.empty_like(x_cls)
     d_aux = torch.empty_like(x_aux)
     ws = torch.empty(int(lib().apb_tlce_workspace_floats(B, N)), device=x_aux.device, dtype=torch.float32)
+    ticket = _tlce_ticket(x_aux.device) if single_launch else None
     check(lib().apb_tlce_fwd_bwd(_p(x_cls), _p(x_aux), _p(target), int(is3d), B, N, Cc, int(box_area), _p(box_dev), w_cls, w_dense,
-                                 _p(loss), _p(d_cls), _p(d_aux), _p(ws), dt(x_aux), _st()), 'tlce_fwd_bwd')
+                                 _p(loss), _p(d_cls), _p(d_aux), _p(ws), _p(ticket), dt(x_aux), _st()), 'tlce_fwd_bwd')
     return loss, d_cls, d_aux
 
 

@@ -63,11 +63,14 @@ int apb_outlook_bwd_mma(const void* v, const void* logits, const void* dy, void*
 /* ---- TokenLabelCrossEntropy forward + gradient in one pass  (loss/cross_entropy.py:136-156, :30-36)
  * x_cls [B,C], x_aux [B,N,C] (dtype); target fp32 [B,C,2+N] (target_is_3d=1) or [B,C] (0);
  * box_area = (bbx2-bbx1)*(bby2-bby1); loss: 1 float; d_cls/d_aux: gradients for upstream gradient 1.
- * workspace: apb_tlce_workspace_floats(B,N) floats. */
+ * workspace: apb_tlce_workspace_floats(B,N) floats.
+ * ticket: optional DEVICE int32, ZERO on entry and private to the stream (the kernel leaves it zero): with it the
+ * class-major fast path is ONE launch -- dense tiles, class-token rows and a last-CTA reduction of the per-CTA loss
+ * partials in a fixed order; NULL = three launches (dense, class tokens, reduce).  Same bits either way. */
 long long apb_tlce_workspace_floats(int B, int N);
 int apb_tlce_fwd_bwd(const void* x_cls, const void* x_aux, const float* target, int target_is_3d, int B, int N, int C,
                      int box_area, const int* box_dev, float w_cls, float w_dense, float* loss, void* d_cls, void* d_aux,
-                     float* workspace, int dtype, apb_stream_t stream);
+                     float* workspace, int* ticket, int dtype, apb_stream_t stream);
 /* box_dev: optional DEVICE int[4] (bbx1,bby1,bbx2,bby2) read by the kernel instead of box_area, so a captured CUDA
  * graph sees a fresh mix-token box on every replay. */
 int apb_scale_by_scalar(const void* in, void* out, long long n, const float* scalar, int dtype, apb_stream_t stream);

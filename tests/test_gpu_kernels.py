@@ -143,6 +143,10 @@ def test_tlce(cfg, dtype):
             continue
         loss_ref, dc_ref, da_ref = O.token_label_ce_grads(xc, xa, bbox, t.double(), wd, wc)
         loss, dc, da = K.tlce_fwd_bwd(xc.to(dev, dtype), xa.to(dev, dtype), t.to(dev), area, wc, wd)
+        # the single-launch form (ticket + last-CTA reduce) and the three-launch form give the same bits, call after call
+        for single in (False, True, True):
+            l2, dc2, da2 = K.tlce_fwd_bwd(xc.to(dev, dtype), xa.to(dev, dtype), t.to(dev), area, wc, wd, single_launch=single)
+            assert torch.equal(l2, loss) and torch.equal(dc2, dc) and torch.equal(da2, da)
         tl = tol(dtype)
         assert abs(float(loss) - float(loss_ref)) < 2e-6 * abs(float(loss_ref)) + 1e-7
         assert rel(da, da_ref) < tl, rel(da, da_ref)
