@@ -145,6 +145,46 @@ def test_volo_d1_full_size_step_runs_and_is_deterministic():
     assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
 
 
+def test_opt_in_launch_modes_are_bit_identical():
+    """The opt-in / switchable launch modes change scheduling only: programmatic dependent launch (apb_set_pdl), the wgrad
+    side stream (ops.SIDE_WGRAD) and the four-stage GEMM kernels must reproduce the default path's loss and every gradient
+    bit for bit (volo_d1 @ 224, bf16)."""
+    from autoprog_b200 import kernels as K, ops
+    dev = need_gpu()
+    torch.manual_seed(0)
+    m = A.create_model('volo_d1', img_size=224).to(dev)
+    x = torch.randn(4, 3, 224, 224, device=dev)
+    tgt = torch.softmax(torch.randn(4, 1000, 198, device=dev), 1)
+    crit = A.TokenLabelCrossEntropy(dense_weight=0.5)
+
+    def run():
+        np.random.seed(0)
+        m.zero_grad(set_to_none=True)
+        with A.autocast():
+            loss = crit(m(x), tgt)
+        loss.backward()
+        torch.cuda.synchronize()
+        return loss.item(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+
+    base = run()
+    side = ops.SIDE_WGRAD
+    try:
+        for name, enter, leave in [('pdl', lambda: K.set_pdl(True), lambda: K.set_pdl(False)),
+                                   ('no side stream', lambda: setattr(ops, 'SIDE_WGRAD', False), lambda: setattr(ops, 'SIDE_WGRAD', side)),
+                                   ('4-stage gemm', lambda: K.debug_gemm_switches(0, False), lambda: K.debug_gemm_switches(0, True))]:
+            enter()
+            try:
+                loss, grads = run()
+            finally:
+                leave()
+            assert loss == base[0], name
+            assert grads.keys() == base[1].keys(), name
+            bad = [k for k in grads if not torch.equal(grads[k], base[1][k])]
+            assert not bad, (name, bad[:5])
+    finally:
+        K.set_pdl(False); K.debug_gemm_switches(0, True); ops.SIDE_WGRAD = side
+
+
 @pytest.mark.parametrize('bf16', [False, True])
 def test_deit_against_oracle(bf16):
     """DeiT (timm ViT restated; parity unpinned upstream): kernels vs oracle.vit_forward on a small config, incl. elastic depth."""
