@@ -40,7 +40,9 @@ int apb_outlook_bwd(const void* v, const void* logits, const void* dy, void* dv,
 // logged (apb_fallback_count).
 int apb_mhsa_fwd(const void* qkv, void* out, float* lse, int B, int N, int heads, int D, float scale, int dtype,
                  apb_stream_t stream) {
-  if (dtype == APB_BF16 && D == 32 && B > 0 && N > 0 && N <= 224 && heads > 0) {
+  // (forward only: below ~80 tokens a 128-row query tile is mostly padding and the mma.sync kernel wins -- 14.7 vs 18.9 us at
+  //  N = 64, the 8 x 8 grid of the first AutoProg stage; from N = 100 on the tcgen05 kernel is ahead, 25.0 vs 34.3 us)
+  if (dtype == APB_BF16 && D == 32 && B > 0 && N >= 80 && N <= 224 && heads > 0) {
     const int rc = apb_mhsa_fwd_tc(qkv, out, lse, B, N, heads, D, scale, stream);
     if (rc != APB_ERR_UNSUPPORTED) return rc;
   }
