@@ -68,16 +68,6 @@ __device__ __forceinline__ void phi_fast(float x, float& cdf, float& e) {
   const float half_tail = 0.5f * poly * t * e;          // 0.5 * (1 - erf(z))
   cdf = x >= 0.f ? 1.f - half_tail : half_tail;
 }
-__device__ __forceinline__ float gelu_f(float x) {
-  float cdf, e;
-  phi_fast(x, cdf, e);
-  return x * cdf;
-}
-__device__ __forceinline__ float dgelu_f(float x) {
-  float cdf, e;
-  phi_fast(x, cdf, e);
-  return fmaf(x * 0.39894228040143267794f, e, cdf);
-}
 
 // AUX = the epilogue needs the per-warp gelu' boxes (GELU / dGELU).  Without them the shared memory they would take
 // becomes one more pipeline stage: the main loop is bound by bytes in flight from L2, not by the tensor pipe.
