@@ -255,11 +255,14 @@ __device__ __forceinline__ float ca_block_reduce(float v, float* red, bool is_ma
 
 constexpr int CA_MAXD = 64;
 // CD = compile-time head dim (32: every VOLO variant; 64) so the per-key row lives in registers; 0 = runtime D
+// kv0 / dkv0 != nullptr: SPLIT layout -- key 0 (the class token itself) lives in kv0 [B, 2C] and keys 1 .. N-1 (the patch
+// tokens) in kv [B, N-1, 2C], so the caller never has to concatenate [cls ; tokens] into one buffer
 template <typename T, bool BWD, int CD>
 __global__ void __launch_bounds__(128) class_attn_kernel(const T* __restrict__ q, const T* __restrict__ kv,
                                                          const T* __restrict__ dout, T* __restrict__ out,
                                                          T* __restrict__ dq, T* __restrict__ dkv, int B, int N, int heads,
-                                                         int Drt, float scale) {
+                                                         int Drt, float scale, const T* __restrict__ kv0,
+                                                         T* __restrict__ dkv0) {
   const int D = CD ? CD : Drt;
   extern __shared__ float sm[];
   float* sP = sm;                 // [N] probabilities
@@ -271,8 +274,11 @@ __global__ void __launch_bounds__(128) class_attn_kernel(const T* __restrict__ q
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bh = blockIdx.x, b = bh / heads, hd = bh % heads;
   const size_t tok = (size_t)2 * heads * D;
-  const T* kb = kv + (size_t)b * N * tok + (size_t)hd * D;
-  const T* vb = kb + (size_t)heads * D;
+  const int sp = kv0 != nullptr ? 1 : 0;                      // split layout: key 0 comes from kv0
+  const T* kb = kv + (size_t)b * (N - sp) * tok + (size_t)hd * D - (size_t)sp * tok;      // kb + k * tok is key k >= sp
+  const T* kb0 = sp ? kv0 + (size_t)b * tok + (size_t)hd * D : kb;                         // key 0
+  const size_t voff = (size_t)heads * D;
+  auto krow = [&](int k) -> const T* { return k == 0 ? kb0 : kb + (size_t)k * tok; };
   const size_t qoff = (size_t)b * heads * D + (size_t)hd * D;
   for (int c = tid; c < D; c += 128) {
     sQ[c] = to_f(q[qoff + c]) * scale;
@@ -283,7 +289,7 @@ __global__ void __launch_bounds__(128) class_attn_kernel(const T* __restrict__ q
   // ---- scores and softmax
   float m = -INFINITY;
   for (int k = tid; k < N; k += 128) {
-    ca_load_row(kb + (size_t)k * tok, D, row);
+    ca_load_row(krow(k), D, row);
     float a = 0.f;
 #pragma unroll
     for (int c = 0; c < D; ++c) a = fmaf(sQ[c], row[c], a);
@@ -299,7 +305,7 @@ __global__ void __launch_bounds__(128) class_attn_kernel(const T* __restrict__ q
   float dsum = 0.f;
   if (BWD) {
     for (int k = tid; k < N; k += 128) {
-      ca_load_row(vb + (size_t)k * tok, D, row);
+      ca_load_row(krow(k) + voff, D, row);
       float dp = 0.f;
 #pragma unroll
       for (int c = 0; c < D; ++c) dp = fmaf(sG[c], row[c], dp);
@@ -307,29 +313,30 @@ __global__ void __launch_bounds__(128) class_attn_kernel(const T* __restrict__ q
       dsum = fmaf(sP[k], dp, dsum);
     }
     dsum = ca_block_reduce(dsum, red, false);
-    T* dkb = dkv + (size_t)b * N * tok + (size_t)hd * D;
-    T* dvb = dkb + (size_t)heads * D;
+    T* dkb = dkv + (size_t)b * (N - sp) * tok + (size_t)hd * D - (size_t)sp * tok;
+    T* dkb0 = sp ? dkv0 + (size_t)b * tok + (size_t)hd * D : dkb;
     for (int k = tid; k < N; k += 128) {
       const float ds = sP[k] * (sS[k] - dsum);
       sS[k] = ds;
-      ca_store_row(dkb + (size_t)k * tok, D, sQ, ds);          // dK[k] = dS[k] * (q * scale)
-      ca_store_row(dvb + (size_t)k * tok, D, sG, sP[k]);       // dV[k] = P[k] * dO
+      T* drow = k == 0 ? dkb0 : dkb + (size_t)k * tok;
+      ca_store_row(drow, D, sQ, ds);                           // dK[k] = dS[k] * (q * scale)
+      ca_store_row(drow + voff, D, sG, sP[k]);                 // dV[k] = P[k] * dO
     }
   }
   __syncthreads();
   // ---- per-channel sums over keys: out[c] = sum_k P[k] V[k][c]  /  dq[c] = scale * sum_k dS[k] K[k][c]
   const float* wgt = BWD ? sS : sP;
-  const T* src = BWD ? kb : vb;
+  const size_t soff = BWD ? 0 : voff;
   for (int c0 = 0; c0 < D; c0 += 32) {
     const int c = c0 + lane;
     float a0 = 0.f, a1 = 0.f;
     if (c < D) {
       int k = warp;
       for (; k + 4 < N; k += 8) {
-        a0 = fmaf(wgt[k], to_f(src[(size_t)k * tok + c]), a0);
-        a1 = fmaf(wgt[k + 4], to_f(src[(size_t)(k + 4) * tok + c]), a1);
+        a0 = fmaf(wgt[k], to_f(krow(k)[soff + c]), a0);
+        a1 = fmaf(wgt[k + 4], to_f(krow(k + 4)[soff + c]), a1);
       }
-      if (k < N) a0 = fmaf(wgt[k], to_f(src[(size_t)k * tok + c]), a0);
+      if (k < N) a0 = fmaf(wgt[k], to_f(krow(k)[soff + c]), a0);
       sAcc[warp * D + c] = a0 + a1;
     }
   }
@@ -391,46 +398,56 @@ int apb_mhsa_bwd_simt(const void* qkv, const void* out, const void* dout, const 
   return 0;
 }
 
-int apb_class_attn_fwd(const void* q, const void* kv, void* out, int B, int N, int heads, int D, float scale, int dtype,
-                       apb_stream_t stream) {
-  cudaStream_t st = APB_STREAM(stream);
-  APB_CHECK_ARG(B > 0 && N > 0 && heads > 0 && D > 0, APB_ERR_SHAPE, "class_attn_fwd: bad shape");
+// one launcher for both directions and both key layouts (kv0 == nullptr: keys [B, N, 2C] in kv; else split, see the kernel)
+template <bool BWD>
+static int class_attn_launch(const void* q, const void* kv0, const void* kv, const void* dout, void* out, void* dq, void* dkv0,
+                             void* dkv, int B, int N, int heads, int D, float scale, int dtype, cudaStream_t st) {
+  const char* name = BWD ? "class_attn_bwd" : "class_attn_fwd";
+  APB_CHECK_ARG(B > 0 && N > 0 && heads > 0 && D > 0, APB_ERR_SHAPE, "%s: bad shape", name);
+  APB_CHECK_ARG(kv0 == nullptr || N >= 2, APB_ERR_SHAPE, "%s: the split layout needs at least one token besides the class token", name);
   const size_t smem = (size_t)(2 * N + 6 * D + 4) * sizeof(float);
   APB_CHECK_ARG(smem <= 227 * 1024 && D <= CA_MAXD && D % 8 == 0, APB_ERR_UNSUPPORTED, "class_attn: N=%d D=%d unsupported", N, D);
   const int grid = B * heads;
-#define CA_LAUNCH(T_, CD_, ARGS_)                                                                                  \
-  do {                                                                                                             \
-    cudaFuncSetAttribute(class_attn_kernel<T_, false, CD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-    class_attn_kernel<T_, false, CD_><<<grid, 128, smem, st>>> ARGS_;                                                 \
+#define CA_LAUNCH(T_, CD_)                                                                                            \
+  do {                                                                                                                \
+    cudaFuncSetAttribute(class_attn_kernel<T_, BWD, CD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    class_attn_kernel<T_, BWD, CD_><<<grid, 128, smem, st>>>((const T_*)q, (const T_*)kv, (const T_*)dout, (T_*)out, (T_*)dq, \
+                                                             (T_*)dkv, B, N, heads, D, scale, (const T_*)kv0, (T_*)dkv0); \
   } while (0)
-  if (dtype == APB_F32) {
-    if (D == 32) CA_LAUNCH(float, 32, ((const float*)q, (const float*)kv, nullptr, (float*)out, nullptr, nullptr, B, N, heads, D, scale)); else if (D == 64) CA_LAUNCH(float, 64, ((const float*)q, (const float*)kv, nullptr, (float*)out, nullptr, nullptr, B, N, heads, D, scale)); else CA_LAUNCH(float, 0, ((const float*)q, (const float*)kv, nullptr, (float*)out, nullptr, nullptr, B, N, heads, D, scale));
-  } else if (dtype == APB_BF16) {
-    if (D == 32) CA_LAUNCH(bf16, 32, ((const bf16*)q, (const bf16*)kv, nullptr, (bf16*)out, nullptr, nullptr, B, N, heads, D, scale)); else if (D == 64) CA_LAUNCH(bf16, 64, ((const bf16*)q, (const bf16*)kv, nullptr, (bf16*)out, nullptr, nullptr, B, N, heads, D, scale)); else CA_LAUNCH(bf16, 0, ((const bf16*)q, (const bf16*)kv, nullptr, (bf16*)out, nullptr, nullptr, B, N, heads, D, scale));
-  } else { apb_set_error("class_attn: dtype %d", dtype); return APB_ERR_DTYPE; }
+#define CA_DISPATCH(T_)            \
+  do {                             \
+    if (D == 32) CA_LAUNCH(T_, 32); \
+    else if (D == 64) CA_LAUNCH(T_, 64); \
+    else CA_LAUNCH(T_, 0);         \
+  } while (0)
+  if (dtype == APB_F32) CA_DISPATCH(float);
+  else if (dtype == APB_BF16) CA_DISPATCH(bf16);
+  else { apb_set_error("class_attn: dtype %d", dtype); return APB_ERR_DTYPE; }
+#undef CA_DISPATCH
 #undef CA_LAUNCH
-  APB_LAUNCH_CHECK("class_attn_fwd");
+  APB_LAUNCH_CHECK(name);
   return 0;
+}
+
+int apb_class_attn_fwd(const void* q, const void* kv, void* out, int B, int N, int heads, int D, float scale, int dtype,
+                       apb_stream_t stream) {
+  return class_attn_launch<false>(q, nullptr, kv, nullptr, out, nullptr, nullptr, nullptr, B, N, heads, D, scale, dtype, APB_STREAM(stream));
 }
 
 int apb_class_attn_bwd(const void* q, const void* kv, const void* dout, void* dq, void* dkv, int B, int N, int heads,
                        int D, float scale, int dtype, apb_stream_t stream) {
-  cudaStream_t st = APB_STREAM(stream);
-  APB_CHECK_ARG(B > 0 && N > 0 && heads > 0 && D > 0, APB_ERR_SHAPE, "class_attn_bwd: bad shape");
-  const size_t smem = (size_t)(2 * N + 6 * D + 4) * sizeof(float);
-  APB_CHECK_ARG(smem <= 227 * 1024 && D <= CA_MAXD && D % 8 == 0, APB_ERR_UNSUPPORTED, "class_attn: N=%d D=%d unsupported", N, D);
-  const int grid = B * heads;
-#define CA_LAUNCH(T_, CD_, ARGS_)                                                                                  \
-  do {                                                                                                             \
-    cudaFuncSetAttribute(class_attn_kernel<T_, true, CD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-    class_attn_kernel<T_, true, CD_><<<grid, 128, smem, st>>> ARGS_;                                                 \
-  } while (0)
-  if (dtype == APB_F32) {
-    if (D == 32) CA_LAUNCH(float, 32, ((const float*)q, (const float*)kv, (const float*)dout, nullptr, (float*)dq, (float*)dkv, B, N, heads, D, scale)); else if (D == 64) CA_LAUNCH(float, 64, ((const float*)q, (const float*)kv, (const float*)dout, nullptr, (float*)dq, (float*)dkv, B, N, heads, D, scale)); else CA_LAUNCH(float, 0, ((const float*)q, (const float*)kv, (const float*)dout, nullptr, (float*)dq, (float*)dkv, B, N, heads, D, scale));
-  } else if (dtype == APB_BF16) {
-    if (D == 32) CA_LAUNCH(bf16, 32, ((const bf16*)q, (const bf16*)kv, (const bf16*)dout, nullptr, (bf16*)dq, (bf16*)dkv, B, N, heads, D, scale)); else if (D == 64) CA_LAUNCH(bf16, 64, ((const bf16*)q, (const bf16*)kv, (const bf16*)dout, nullptr, (bf16*)dq, (bf16*)dkv, B, N, heads, D, scale)); else CA_LAUNCH(bf16, 0, ((const bf16*)q, (const bf16*)kv, (const bf16*)dout, nullptr, (bf16*)dq, (bf16*)dkv, B, N, heads, D, scale));
-  } else { apb_set_error("class_attn: dtype %d", dtype); return APB_ERR_DTYPE; }
-#undef CA_LAUNCH
-  APB_LAUNCH_CHECK("class_attn_bwd");
-  return 0;
+  return class_attn_launch<true>(q, nullptr, kv, dout, nullptr, dq, nullptr, dkv, B, N, heads, D, scale, dtype, APB_STREAM(stream));
+}
+
+// split key layout: the class token's own k / v row in kv_cls [B, 2C], the N - 1 patch tokens in kv_tok [B, N-1, 2C]
+int apb_class_attn_fwd_split(const void* q, const void* kv_cls, const void* kv_tok, void* out, int B, int N, int heads, int D,
+                             float scale, int dtype, apb_stream_t stream) {
+  APB_CHECK_ARG(kv_cls != nullptr, APB_ERR_ARG, "class_attn_fwd_split: kv_cls is required");
+  return class_attn_launch<false>(q, kv_cls, kv_tok, nullptr, out, nullptr, nullptr, nullptr, B, N, heads, D, scale, dtype, APB_STREAM(stream));
+}
+
+int apb_class_attn_bwd_split(const void* q, const void* kv_cls, const void* kv_tok, const void* dout, void* dq, void* dkv_cls,
+                             void* dkv_tok, int B, int N, int heads, int D, float scale, int dtype, apb_stream_t stream) {
+  APB_CHECK_ARG(kv_cls != nullptr && dkv_cls != nullptr, APB_ERR_ARG, "class_attn_bwd_split: kv_cls / dkv_cls are required");
+  return class_attn_launch<true>(q, kv_cls, kv_tok, dout, nullptr, dq, dkv_cls, dkv_tok, B, N, heads, D, scale, dtype, APB_STREAM(stream));
 }

@@ -76,6 +76,7 @@ class FlatGroup:
         self.flat_g.zero_()
         for p in self.params:
             p.grad = None
+            p._apb_grad_claimed = False        # ops.grad_dest hands the view out once per backward
 
 
 class FlatState:

@@ -252,6 +252,27 @@ def class_attn_bwd(q, kv, dout, heads: int, scale: float):
     return dq, dkv
 
 
+def class_attn_fwd_split(q, kv_cls, kv_tok, heads: int, scale: float):
+    """Keys in two buffers: kv_cls [B, 2C] (the class token, key 0) and kv_tok [B, N-1, 2C] (the patch tokens)."""
+    B, Nt, C2 = kv_tok.shape
+    D = C2 // (2 * heads)
+    out = torch.empty_like(q)
+    check(lib().apb_class_attn_fwd_split(_p(q), _p(kv_cls), _p(kv_tok), _p(out), B, Nt + 1, heads, D, scale, dt(q), _st()),
+          'class_attn_fwd_split')
+    return out
+
+
+def class_attn_bwd_split(q, kv_cls, kv_tok, dout, heads: int, scale: float):
+    B, Nt, C2 = kv_tok.shape
+    D = C2 // (2 * heads)
+    dq = torch.empty_like(q)
+    dkv_cls = torch.empty_like(kv_cls)
+    dkv_tok = torch.empty_like(kv_tok)
+    check(lib().apb_class_attn_bwd_split(_p(q), _p(kv_cls), _p(kv_tok), _p(dout), _p(dq), _p(dkv_cls), _p(dkv_tok), B, Nt + 1,
+                                         heads, D, scale, dt(q), _st()), 'class_attn_bwd_split')
+    return dq, dkv_cls, dkv_tok
+
+
 # ------------------------------------------------------------------ elementwise / layout
 def avgpool2_fwd(x):
     B, H, W, Cc = x.shape

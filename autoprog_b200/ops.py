@@ -97,10 +97,17 @@ def _lin_fwd(x2d, w, bias, epilogue=K.EPI_NONE):
 
 def grad_dest(p):
     """Flat-gradient view a kernel may write this parameter's gradient into (see flat.FlatGroup): only when the
-    parameter has no `.grad` yet -- i.e. not while gradients are being accumulated over several backward passes."""
+    parameter has no `.grad` yet -- i.e. not while gradients are being accumulated over several backward passes -- and
+    only ONCE per backward: a parameter used twice in one forward (e.g. ClassAttention.kv on the class token and on the
+    patch tokens) gets its second contribution as a fresh tensor that autograd adds to the first (`.grad` is still None
+    while the engine collects both, so without the claim the second kernel would overwrite the first one's output)."""
     if p is None or p.grad is not None:
         return None
-    return getattr(p, '_apb_grad_view', None)
+    v = getattr(p, '_apb_grad_view', None)
+    if v is None or getattr(p, '_apb_grad_claimed', False):
+        return None
+    p._apb_grad_claimed = True
+    return v
 
 
 # The weight-gradient GEMM (+ its split-K reduce) of a Linear does not depend on the input-gradient GEMM: with
@@ -286,6 +293,24 @@ class ClassAttnCoreFn(torch.autograd.Function):
         heads, scale = ctx.cfg
         dq, dkv = K.class_attn_bwd(q, kv, K.cast(_c(dout), q.dtype), heads, scale)
         return dq, dkv, None, None
+
+
+class ClassAttnCoreSplitFn(torch.autograd.Function):
+    """cls-query attention with the keys kept in two buffers: q [B,C], kv_cls [B,2C] (key 0), kv_tok [B,N-1,2C] -> [B,C]."""
+
+    @staticmethod
+    def forward(ctx, q, kv_cls, kv_tok, heads, scale):
+        q, kv_cls, kv_tok = _c(q), _c(kv_cls), _c(kv_tok)
+        ctx.save_for_backward(q, kv_cls, kv_tok)
+        ctx.cfg = (heads, scale)
+        return K.class_attn_fwd_split(q, kv_cls, kv_tok, heads, scale)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, kv_cls, kv_tok = ctx.saved_tensors
+        heads, scale = ctx.cfg
+        dq, dkc, dkt = K.class_attn_bwd_split(q, kv_cls, kv_tok, K.cast(_c(dout), q.dtype), heads, scale)
+        return dq, dkc, dkt, None, None
 
 
 class AvgPool2Fn(torch.autograd.Function):

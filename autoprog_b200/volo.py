@@ -288,6 +288,16 @@ class ClassAttention(nn.Module):
         o = ops.ClassAttnCoreFn.apply(q, kv, self.num_heads, self.scale)
         return self.proj(o).reshape(B, 1, -1)
 
+    def forward_pair(self, n_cls, n_tok):
+        """Same arithmetic with the (normalised) class token [B,1,C] and patch tokens [B,N,C] kept in two tensors: the k / v
+        rows of both come from the same Linear, the attention kernel reads key 0 from one buffer and keys 1.. from the other."""
+        B = n_tok.shape[0]
+        kv_tok = self.kv(n_tok)
+        kv_cls = self.kv(n_cls).reshape(B, -1)
+        q = self.q(n_cls.reshape(B, -1))
+        o = ops.ClassAttnCoreSplitFn.apply(q, kv_cls, kv_tok, self.num_heads, self.scale)
+        return self.proj(o).reshape(B, 1, -1)
+
 
 class ClassBlock(nn.Module):
     """models/volo.py:280-308: only the cls row is updated."""
@@ -310,6 +320,14 @@ class ClassBlock(nn.Module):
         cls = cls + self.drop_path(self.attn(self.norm1(xt))).to(cls.dtype)
         cls = cls + self.drop_path(self.mlp(self.norm2(cls))).to(cls.dtype)
         return _JoinCls.apply(cls, xt, 1)
+
+    def forward_pair(self, cls, tok):
+        """The reference's forward on (cls [B,1,C], tok [B,N,C]) instead of cat([cls, tok]): only the class row changes in a
+        ClassBlock, so the model carries it separately and never copies the N patch tokens (models/volo.py:300-308 slices
+        and re-concatenates them in every block; LayerNorm is row-wise, so norm1 on the two parts is the same arithmetic)."""
+        cls = cls + self.drop_path(self.attn.forward_pair(self.norm1(cls), self.norm1(tok))).to(cls.dtype)
+        cls = cls + self.drop_path(self.mlp(self.norm2(cls))).to(cls.dtype)
+        return cls
 
 
 class _SplitCls(torch.autograd.Function):
@@ -614,6 +632,13 @@ class VOLO(nn.Module):
             x = block(x)
         return x
 
+    def forward_cls_pair(self, tok):
+        """forward_cls without ever building cat([cls, tokens]): returns the final class token [B,1,C]."""
+        cls = self.cls_token.expand(tok.shape[0], -1, -1).to(tok.dtype).contiguous()
+        for block in self.post_network:
+            cls = block.forward_pair(cls, tok)
+        return cls
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError('autoprog_b200.VOLO runs on CUDA (sm_100a) only; there is no CPU fallback')
@@ -639,16 +664,24 @@ class VOLO(nn.Module):
             bbx1, bby1, bbx2, bby2 = 0, 0, 0, 0
 
         x = self.forward_tokens(x)
-        if self.post_network is not None:
-            x = self.forward_cls(x)
-        x = self.norm(x)
-
-        if self.return_mean:
-            return self.head(x.float().mean(1).to(x.dtype))
-        x_cls = self.head(x[:, 0])
-        if not self.return_dense:
-            return x_cls
-        x_aux = self.aux_head(x[:, 1:])
+        if (self.post_network is not None and not self.return_mean
+                and all(isinstance(b, ClassBlock) for b in self.post_network)):
+            # class token and patch tokens stay two tensors through the class blocks, the final norm and the two heads
+            cls = self.forward_cls_pair(x)
+            x_cls = self.head(self.norm(cls).reshape(cls.shape[0], -1))
+            if not self.return_dense:
+                return x_cls
+            x_aux = self.aux_head(self.norm(x))
+        else:
+            if self.post_network is not None:
+                x = self.forward_cls(x)
+            x = self.norm(x)
+            if self.return_mean:
+                return self.head(x.float().mean(1).to(x.dtype))
+            x_cls = self.head(x[:, 0])
+            if not self.return_dense:
+                return x_cls
+            x_aux = self.aux_head(x[:, 1:])
         if not self.training:
             return x_cls + 0.5 * x_aux.max(1)[0]
         if self.mix_token and self.training:

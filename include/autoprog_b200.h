@@ -175,6 +175,13 @@ int apb_class_attn_fwd(const void* q, const void* kv, void* out, int B, int N, i
                        apb_stream_t stream);
 int apb_class_attn_bwd(const void* q, const void* kv, const void* dout, void* dq, void* dkv, int B, int N, int heads,
                        int D, float scale, int dtype, apb_stream_t stream);
+/* the same with the keys in two buffers -- kv_cls [B, 2*heads*D] = the class token's own k / v row (key 0), kv_tok
+ * [B, N-1, 2*heads*D] = the patch tokens (keys 1 .. N-1): the caller keeps [cls] and [tokens] apart instead of building
+ * cat([cls, tokens]) for every ClassBlock (models/volo.py:300-308). */
+int apb_class_attn_fwd_split(const void* q, const void* kv_cls, const void* kv_tok, void* out, int B, int N, int heads, int D,
+                             float scale, int dtype, apb_stream_t stream);
+int apb_class_attn_bwd_split(const void* q, const void* kv_cls, const void* kv_tok, const void* dout, void* dq, void* dkv_cls,
+                             void* dkv_tok, int B, int N, int heads, int D, float scale, int dtype, apb_stream_t stream);
 
 /* ---- elementwise / layout kernels
  * avgpool2: AvgPool2d(2,2,ceil_mode=True) on NHWC (models/volo.py:75,87) and its transpose.

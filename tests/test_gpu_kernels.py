@@ -275,6 +275,13 @@ def test_class_attn_core(B, N, heads, D, dtype):
     dq, dkv = K.class_attn_bwd(qq.detach().to(dev, dtype), kv.detach().to(dev, dtype), do.to(dev, dtype), heads, D ** -0.5)
     t = tol(dtype)
     assert rel(out, ref) < t and rel(dq, qq.grad) < t and rel(dkv, kv.grad) < t
+    # split key layout (class token row and patch-token rows in two buffers): the same bits as the concatenated layout
+    kvd = kv.detach().to(dev, dtype)
+    kc, kt = kvd[:, 0].contiguous(), kvd[:, 1:].contiguous()
+    out2 = K.class_attn_fwd_split(qq.detach().to(dev, dtype), kc, kt, heads, D ** -0.5)
+    dq2, dkc, dkt = K.class_attn_bwd_split(qq.detach().to(dev, dtype), kc, kt, do.to(dev, dtype), heads, D ** -0.5)
+    assert torch.equal(out2, out) and torch.equal(dq2, dq)
+    assert torch.equal(dkc, dkv[:, 0]) and torch.equal(dkt, dkv[:, 1:])
 
 
 @pytest.mark.parametrize('dtype', DT)
