@@ -288,6 +288,7 @@ def probe_throughput(model, loss_fn, x: torch.Tensor, target: torch.Tensor, conf
     def fwd_bwd():
         for p, _ in saved:
             p.grad = None
+            p._apb_grad_claimed = False          # see ops.grad_dest: the flat view may be handed out again
         with ops.autocast(enabled=bf16):
             out = model(x)
             loss = loss_fn(out[0] if isinstance(out, tuple) else out, target)
