@@ -271,3 +271,29 @@ def test_flat_state_grouping_alignment_and_views():
     for g in flat.groups:
         for n, p, o in zip(g.names, g.params, g.offsets):
             assert p.grad.data_ptr() == g.flat_g[o:].data_ptr() and torch.equal(p.grad, auto[n])
+
+
+def test_grad_dest_hands_the_flat_view_out_once_per_backward():
+    """ops.grad_dest: a kernel may write a parameter's gradient straight into its flat-buffer view only ONCE per backward.
+    `.grad` stays None while autograd collects the contributions of a parameter that is used twice in one forward (e.g.
+    ClassAttention.kv on the class token and on the patch tokens), so a second hand-out would let the second kernel
+    overwrite the first one's output; zero_grad re-arms the view, an existing `.grad` (accumulation steps) blocks it."""
+    import torch
+    import torch.nn as nn
+    from autoprog_b200 import ops
+    from autoprog_b200.flat import FlatState
+
+    net = nn.Linear(4, 4)
+    flat = FlatState(net, weight_decay=0.05, want_shadow=False)
+    flat.zero_grad()
+    w = net.weight
+    first = ops.grad_dest(w)
+    assert first is not None and first.data_ptr() == w._apb_grad_view.data_ptr()
+    assert ops.grad_dest(w) is None                       # second use in the same backward: autograd accumulates instead
+    flat.zero_grad()
+    assert ops.grad_dest(w) is not None                   # re-armed by the next step's zero_grad
+    flat.zero_grad()
+    w.grad = torch.zeros_like(w)
+    assert ops.grad_dest(w) is None                       # gradient accumulation over several backward passes
+    assert ops.grad_dest(None) is None
+    assert ops.grad_dest(nn.Parameter(torch.zeros(2))) is None     # not managed by a FlatState
